@@ -1,0 +1,206 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle for maxwell_b200 (see mxo_geom.hpp header).
+// C entry points so tests/ and bench.py's cpu_baseline leg can drive the oracle via ctypes.
+#include <cstring>
+#include <omp.h>
+
+#include "mxo_ops.hpp"
+
+using namespace mxo;
+
+namespace {
+thread_local std::string g_err;
+struct Mat {
+  bool cplx_ = false;
+  Csr<double> r;
+  Csr<cplx> c;
+};
+template <class F> int guard(F&& f) {
+  try { f(); return 0; } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+}  // namespace
+
+extern "C" {
+
+const char* mxo_last_error() { return g_err.c_str(); }
+
+// ---- shapes -----------------------------------------------------------------------------
+void* mxo_shape_cylinder(double r, const double axis[3], const double loc[3]) {
+  return new std::shared_ptr<Shape>(new Cylinder(r, {axis[0], axis[1], axis[2]}, {loc[0], loc[1], loc[2]}));
+}
+void* mxo_shape_sphere(double r, const double loc[3]) {
+  return new std::shared_ptr<Shape>(new Sphere(r, {loc[0], loc[1], loc[2]}));
+}
+void* mxo_shape_slab(double thickness, const double n[3], const double loc[3]) {
+  return new std::shared_ptr<Shape>(makeSlab(thickness, {n[0], n[1], n[2]}, {loc[0], loc[1], loc[2]}));
+}
+void* mxo_shape_halfspace(const double point[3], const double n[3]) {
+  return new std::shared_ptr<Shape>(new HalfSpace({point[0], point[1], point[2]}, {n[0], n[1], n[2]}));
+}
+void* mxo_shape_intersection(void* const* shapes, int n) {
+  auto is = std::make_shared<Intersection>();
+  for (int i = 0; i < n; ++i) is->subs.push_back(*static_cast<std::shared_ptr<Shape>*>(shapes[i]));
+  return new std::shared_ptr<Shape>(is);
+}
+void mxo_shape_invert(void* sh) { (*static_cast<std::shared_ptr<Shape>*>(sh))->sign *= -1.0; }
+double mxo_shape_func(void* sh, const double p[3]) { return (*static_cast<std::shared_ptr<Shape>*>(sh))->func({p[0], p[1], p[2]}); }
+void mxo_shape_destroy(void* sh) { delete static_cast<std::shared_ptr<Shape>*>(sh); }
+
+// cut-cell fractions exposed for unit tests: kind 0 = edge (axis), 1 = face (type), 2 = box
+double mxo_fraction(void* sh, int kind, int axis, const double len[3], const double p[3]) {
+  const Shape& s = **static_cast<std::shared_ptr<Shape>*>(sh);
+  const D3 pp{p[0], p[1], p[2]};
+  if (kind == 0) return segmentFraction(s, axis, len[0], pp);
+  if (kind == 1) return rectFraction(s, axis, len[0], len[1], pp);
+  return boxFraction(s, len[0], len[1], len[2], pp);
+}
+
+// ---- simulation -------------------------------------------------------------------------
+void* mxo_sim_create(const int n[3], const double origin[3], const double size[3]) {
+  return new Sim({n[0], n[1], n[2]}, {origin[0], origin[1], origin[2]}, {size[0], size[1], size[2]});
+}
+void mxo_sim_destroy(void* s) { delete static_cast<Sim*>(s); }
+void mxo_sim_set_bcs(void* s, const int lower[3], const int upper[3]) {
+  Sim* sim = static_cast<Sim*>(s);
+  for (int i = 0; i < 3; ++i) { sim->lower[i] = BCType(lower[i]); sim->upper[i] = BCType(upper[i]); }
+}
+void mxo_sim_set_phase_shifts(void* s, const double ph[3]) {
+  Sim* sim = static_cast<Sim*>(s);
+  for (int i = 0; i < 3; ++i) sim->phaseShifts[i] = ph[i];
+}
+void mxo_sim_set_pec(void* s, void* shape) { static_cast<Sim*>(s)->pec = *static_cast<std::shared_ptr<Shape>*>(shape); }
+void mxo_sim_set_literal_upper_periodic_e(void* s, int on) { static_cast<Sim*>(s)->literalUpperPeriodicE = on != 0; }
+int mxo_sim_setup(void* s) { return guard([&] { static_cast<Sim*>(s)->setup(); }); }
+
+static const Field* fieldOf(const Sim* sim, const char* name) {
+  const std::string n(name);
+  if (n == "bfield") return sim->B.get();
+  if (n == "efield") return sim->E.get();
+  if (n == "psifield") return sim->Psi.get();
+  throw std::runtime_error("mxo: unknown field '" + n + "'");
+}
+int64_t mxo_sim_map_size(void* s, const char* field) {
+  int64_t n = -1;
+  guard([&] { n = int64_t(fieldOf(static_cast<Sim*>(s), field)->gids.size()); });
+  return n;
+}
+int mxo_sim_map_copy(void* s, const char* field, int64_t* out) {
+  return guard([&] {
+    const Field* f = fieldOf(static_cast<Sim*>(s), field);
+    std::memcpy(out, f->gids.data(), f->gids.size() * sizeof(int64_t));
+  });
+}
+int64_t mxo_sim_map_num_global(void* s, const char* field) {
+  int64_t n = -1;
+  guard([&] { n = fieldOf(static_cast<Sim*>(s), field)->numGlobal(); });
+  return n;
+}
+// PEC fraction of every DOF in a field's map (1.0 when no PEC)
+int mxo_sim_map_fracs(void* s, const char* field, double* out) {
+  return guard([&] {
+    const Field* f = fieldOf(static_cast<Sim*>(s), field);
+    for (size_t i = 0; i < f->gids.size(); ++i) {
+      I3 cell; int c;
+      cellCompOf(*f, f->gids[i], cell, c);
+      out[i] = f->frac(c, cell, "pec");
+    }
+  });
+}
+
+// ---- operators --------------------------------------------------------------------------
+void* mxo_build_op(void* s, const char* name, int is_complex) {
+  Mat* m = new Mat;
+  m->cplx_ = is_complex != 0;
+  const int rc = guard([&] {
+    if (m->cplx_) m->c = buildOp<cplx>(*static_cast<Sim*>(s), name);
+    else m->r = buildOp<double>(*static_cast<Sim*>(s), name);
+  });
+  if (rc != 0) { delete m; return nullptr; }
+  return m;
+}
+// the reference's real 2n x 2n storage of a complex matrix
+void* mxo_mat_kform(void* h) {
+  Mat* src = static_cast<Mat*>(h);
+  if (!src->cplx_) { g_err = "mxo: kform needs a complex matrix"; return nullptr; }
+  Mat* m = new Mat;
+  m->r = toKForm(src->c);
+  return m;
+}
+void* mxo_mat_multiply(void* a, void* b) {
+  Mat *A = static_cast<Mat*>(a), *B = static_cast<Mat*>(b);
+  Mat* m = new Mat;
+  m->cplx_ = A->cplx_;
+  const int rc = guard([&] {
+    if (A->cplx_ != B->cplx_) throw std::runtime_error("mxo: mixed scalar types");
+    if (A->cplx_) m->c = multiply(A->c, B->c); else m->r = multiply(A->r, B->r);
+  });
+  if (rc != 0) { delete m; return nullptr; }
+  return m;
+}
+void mxo_mat_destroy(void* h) { delete static_cast<Mat*>(h); }
+int mxo_mat_is_complex(void* h) { return static_cast<Mat*>(h)->cplx_ ? 1 : 0; }
+void mxo_mat_shape(void* h, int64_t* nrows, int64_t* ncols, int64_t* nnz) {
+  Mat* m = static_cast<Mat*>(h);
+  if (m->cplx_) { *nrows = m->c.nrows; *ncols = m->c.ncols; *nnz = m->c.nnz(); }
+  else { *nrows = m->r.nrows; *ncols = m->r.ncols; *nnz = m->r.nnz(); }
+}
+// vals: nnz doubles (real) or 2*nnz doubles (complex, interleaved)
+void mxo_mat_copy(void* h, int64_t* rowptr, int32_t* col, double* vals) {
+  Mat* m = static_cast<Mat*>(h);
+  if (m->cplx_) {
+    std::memcpy(rowptr, m->c.rowptr.data(), m->c.rowptr.size() * sizeof(int64_t));
+    std::memcpy(col, m->c.col.data(), m->c.col.size() * sizeof(int32_t));
+    std::memcpy(vals, m->c.val.data(), m->c.val.size() * sizeof(cplx));
+  } else {
+    std::memcpy(rowptr, m->r.rowptr.data(), m->r.rowptr.size() * sizeof(int64_t));
+    std::memcpy(col, m->r.col.data(), m->r.col.size() * sizeof(int32_t));
+    std::memcpy(vals, m->r.val.data(), m->r.val.size() * sizeof(double));
+  }
+}
+void mxo_mat_maps(void* h, int64_t* rowGid, int64_t* colGid) {
+  Mat* m = static_cast<Mat*>(h);
+  const auto& rg = m->cplx_ ? m->c.rowGid : m->r.rowGid;
+  const auto& cg = m->cplx_ ? m->c.colGid : m->r.colGid;
+  if (rowGid) std::memcpy(rowGid, rg.data(), rg.size() * sizeof(int64_t));
+  if (colGid) std::memcpy(colGid, cg.data(), cg.size() * sizeof(int64_t));
+}
+// Y = A X (column-major, ld in scalars). nthreads <= 0 keeps the OpenMP default.
+int mxo_mat_apply(void* h, const double* X, int64_t ldx, double* Y, int64_t ldy, int nvec, int nthreads) {
+  Mat* m = static_cast<Mat*>(h);
+  return guard([&] {
+    const int prev = omp_get_max_threads();
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+    if (m->cplx_) spmm(m->c, reinterpret_cast<const cplx*>(X), ldx, reinterpret_cast<cplx*>(Y), ldy, nvec);
+    else spmm(m->r, X, ldx, Y, ldy, nvec);
+    omp_set_num_threads(prev);
+  });
+}
+int mxo_num_threads() { return omp_get_max_threads(); }
+
+// Generic CSR apply on caller-provided arrays (used for the CPU baseline on sub-blocks)
+int mxo_csr_apply(int64_t nrows, const int64_t* rowptr, const int32_t* col, const double* val, int is_complex,
+                  const double* X, int64_t ldx, double* Y, int64_t ldy, int nvec, int nthreads) {
+  return guard([&] {
+    const int prev = omp_get_max_threads();
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < nrows; ++i) {
+      for (int v = 0; v < nvec; ++v) {
+        if (is_complex) {
+          const cplx* x = reinterpret_cast<const cplx*>(X) + v * ldx;
+          const cplx* a = reinterpret_cast<const cplx*>(val);
+          cplx sum(0.0);
+          for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) sum += a[p] * x[col[p]];
+          reinterpret_cast<cplx*>(Y)[i + v * ldy] = sum;
+        } else {
+          const double* x = X + v * ldx;
+          double sum = 0.0;
+          for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) sum += val[p] * x[col[p]];
+          Y[i + v * ldy] = sum;
+        }
+      }
+    }
+    omp_set_num_threads(prev);
+  });
+}
+
+}  // extern "C"

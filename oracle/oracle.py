@@ -1,0 +1,264 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front end of the CPU oracle (oracle/liboracle.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; the product package maxwell_b200 never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+PERIODIC, ZERO, CONSTANT, PEC, PMC = 0, 1, 2, 3, 4
+
+
+def build():
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        vp, i64, dbl, cp = C.c_void_p, C.c_int64, C.c_double, C.c_char_p
+        d3 = C.POINTER(C.c_double)
+        i3 = C.POINTER(C.c_int)
+        sig = {
+            "mxo_last_error": (cp, []),
+            "mxo_shape_cylinder": (vp, [dbl, d3, d3]),
+            "mxo_shape_sphere": (vp, [dbl, d3]),
+            "mxo_shape_slab": (vp, [dbl, d3, d3]),
+            "mxo_shape_halfspace": (vp, [d3, d3]),
+            "mxo_shape_intersection": (vp, [C.POINTER(vp), C.c_int]),
+            "mxo_shape_invert": (None, [vp]),
+            "mxo_shape_func": (dbl, [vp, d3]),
+            "mxo_shape_destroy": (None, [vp]),
+            "mxo_fraction": (dbl, [vp, C.c_int, C.c_int, d3, d3]),
+            "mxo_sim_create": (vp, [i3, d3, d3]),
+            "mxo_sim_destroy": (None, [vp]),
+            "mxo_sim_set_bcs": (None, [vp, i3, i3]),
+            "mxo_sim_set_phase_shifts": (None, [vp, d3]),
+            "mxo_sim_set_pec": (None, [vp, vp]),
+            "mxo_sim_set_literal_upper_periodic_e": (None, [vp, C.c_int]),
+            "mxo_sim_setup": (C.c_int, [vp]),
+            "mxo_sim_map_size": (i64, [vp, cp]),
+            "mxo_sim_map_copy": (C.c_int, [vp, cp, vp]),
+            "mxo_sim_map_num_global": (i64, [vp, cp]),
+            "mxo_sim_map_fracs": (C.c_int, [vp, cp, vp]),
+            "mxo_build_op": (vp, [vp, cp, C.c_int]),
+            "mxo_mat_kform": (vp, [vp]),
+            "mxo_mat_multiply": (vp, [vp, vp]),
+            "mxo_mat_destroy": (None, [vp]),
+            "mxo_mat_is_complex": (C.c_int, [vp]),
+            "mxo_mat_shape": (None, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+            "mxo_mat_copy": (None, [vp, vp, vp, vp]),
+            "mxo_mat_maps": (None, [vp, vp, vp]),
+            "mxo_mat_apply": (C.c_int, [vp, vp, i64, vp, i64, C.c_int, C.c_int]),
+            "mxo_num_threads": (C.c_int, []),
+            "mxo_csr_apply": (C.c_int, [i64, vp, vp, vp, C.c_int, vp, i64, vp, i64, C.c_int, C.c_int]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def _d3(v):
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+def _i3(v):
+    return (C.c_int * 3)(*[int(x) for x in v])
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(lib().mxo_last_error().decode())
+
+
+class Shape:
+    def __init__(self, handle, keep=()):
+        self.h = handle
+        self._keep = keep
+
+    @staticmethod
+    def cylinder(r, axis, loc):
+        return Shape(lib().mxo_shape_cylinder(r, _d3(axis), _d3(loc)))
+
+    @staticmethod
+    def sphere(r, loc):
+        return Shape(lib().mxo_shape_sphere(r, _d3(loc)))
+
+    @staticmethod
+    def slab(thickness, normal, loc):
+        return Shape(lib().mxo_shape_slab(thickness, _d3(normal), _d3(loc)))
+
+    @staticmethod
+    def halfspace(point, normal):
+        return Shape(lib().mxo_shape_halfspace(_d3(point), _d3(normal)))
+
+    @staticmethod
+    def intersection(shapes):
+        arr = (C.c_void_p * len(shapes))(*[s.h for s in shapes])
+        return Shape(lib().mxo_shape_intersection(arr, len(shapes)), keep=tuple(shapes))
+
+    def func(self, p):
+        return lib().mxo_shape_func(self.h, _d3(p))
+
+    def fraction(self, kind, axis, lens, p):
+        return lib().mxo_fraction(self.h, kind, axis, _d3(list(lens) + [0.0] * (3 - len(lens))), _d3(p))
+
+    def __del__(self):
+        try:
+            lib().mxo_shape_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Matrix:
+    """CSR with local column indices; rows/cols follow the row/col map order."""
+
+    def __init__(self, handle):
+        self.h = handle
+        L = lib()
+        nr, nc, nz = C.c_int64(), C.c_int64(), C.c_int64()
+        L.mxo_mat_shape(handle, C.byref(nr), C.byref(nc), C.byref(nz))
+        self.nrows, self.ncols, self.nnz = nr.value, nc.value, nz.value
+        self.is_complex = bool(L.mxo_mat_is_complex(handle))
+        self._arrays = None
+
+    def arrays(self):
+        if self._arrays is None:
+            rowptr = np.empty(self.nrows + 1, dtype=np.int64)
+            col = np.empty(self.nnz, dtype=np.int32)
+            val = np.empty(self.nnz, dtype=np.complex128 if self.is_complex else np.float64)
+            lib().mxo_mat_copy(self.h, rowptr.ctypes.data, col.ctypes.data, val.ctypes.data)
+            self._arrays = (rowptr, col, val)
+        return self._arrays
+
+    def maps(self):
+        rg = np.empty(self.nrows, dtype=np.int64)
+        cg = np.empty(self.ncols, dtype=np.int64)
+        lib().mxo_mat_maps(self.h, rg.ctypes.data, cg.ctypes.data)
+        return rg, cg
+
+    def scipy(self):
+        import scipy.sparse as sp
+        rowptr, col, val = self.arrays()
+        return sp.csr_matrix((val, col, rowptr), shape=(self.nrows, self.ncols))
+
+    def apply(self, X, nthreads=0):
+        """Y = A X in the reference (Epetra) summation order. X: (ncols,) or (ncols, b) Fortran-ordered."""
+        dt = np.complex128 if self.is_complex else np.float64
+        X2 = np.asfortranarray(np.asarray(X, dtype=dt).reshape(self.ncols, -1))
+        b = X2.shape[1]
+        Y = np.zeros((self.nrows, b), dtype=dt, order="F")
+        _check(lib().mxo_mat_apply(self.h, X2.ctypes.data, self.ncols, Y.ctypes.data, self.nrows, b, nthreads))
+        return Y if np.ndim(X) == 2 else Y[:, 0]
+
+    def kform(self):
+        h = lib().mxo_mat_kform(self.h)
+        if not h:
+            raise RuntimeError(lib().mxo_last_error().decode())
+        return Matrix(h)
+
+    def __matmul__(self, other):
+        h = lib().mxo_mat_multiply(self.h, other.h)
+        if not h:
+            raise RuntimeError(lib().mxo_last_error().decode())
+        return Matrix(h)
+
+    def __del__(self):
+        try:
+            lib().mxo_mat_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Sim:
+    """Mirror of MxEMSim (MxEMSim.cpp:54-225) restricted to 3-D, PEC shapes and BCs."""
+
+    def __init__(self, n, origin=(0.0, 0.0, 0.0), size=(1.0, 1.0, 1.0), lower=None, upper=None,
+                 phase_shifts=None, pec=None, literal_upper_periodic_e=False):
+        if np.isscalar(n):
+            n = (n, n, n)
+        L = lib()
+        self.n = tuple(int(x) for x in n)
+        self.h = L.mxo_sim_create(_i3(n), _d3(origin), _d3(size))
+        if lower is not None or upper is not None:
+            L.mxo_sim_set_bcs(self.h, _i3(lower or (0, 0, 0)), _i3(upper or (0, 0, 0)))
+        if phase_shifts is not None:
+            L.mxo_sim_set_phase_shifts(self.h, _d3(phase_shifts))
+        self.is_complex = phase_shifts is not None and any(p != 0 for p in phase_shifts)
+        self._pec = pec
+        if pec is not None:
+            L.mxo_sim_set_pec(self.h, pec.h)
+        L.mxo_sim_set_literal_upper_periodic_e(self.h, int(literal_upper_periodic_e))
+        _check(L.mxo_sim_setup(self.h))
+
+    def map(self, field):
+        n = lib().mxo_sim_map_size(self.h, field.encode())
+        if n < 0:
+            raise RuntimeError(lib().mxo_last_error().decode())
+        out = np.empty(n, dtype=np.int64)
+        _check(lib().mxo_sim_map_copy(self.h, field.encode(), out.ctypes.data))
+        return out
+
+    def num_global(self, field):
+        return lib().mxo_sim_map_num_global(self.h, field.encode())
+
+    def fracs(self, field):
+        n = lib().mxo_sim_map_size(self.h, field.encode())
+        out = np.empty(n, dtype=np.float64)
+        _check(lib().mxo_sim_map_fracs(self.h, field.encode(), out.ctypes.data))
+        return out
+
+    def op(self, name, is_complex=None):
+        cx = self.is_complex if is_complex is None else is_complex
+        h = lib().mxo_build_op(self.h, name.encode(), int(cx))
+        if not h:
+            raise RuntimeError(lib().mxo_last_error().decode())
+        return Matrix(h)
+
+    def __del__(self):
+        try:
+            lib().mxo_sim_destroy(self.h)
+        except Exception:
+            pass
+
+
+def csr_apply(rowptr, col, val, X, nthreads=0):
+    """Epetra-order CSR apply on raw arrays (CPU baseline on arbitrary row blocks)."""
+    cx = np.iscomplexobj(val)
+    dt = np.complex128 if cx else np.float64
+    nrows = len(rowptr) - 1
+    X2 = np.asfortranarray(np.asarray(X, dtype=dt).reshape(len(X), -1))
+    b = X2.shape[1]
+    Y = np.zeros((nrows, b), dtype=dt, order="F")
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=dt)
+    _check(lib().mxo_csr_apply(nrows, rowptr.ctypes.data, col.ctypes.data, val.ctypes.data, int(cx),
+                               X2.ctypes.data, X2.shape[0], Y.ctypes.data, nrows, b, nthreads))
+    return Y if np.ndim(X) == 2 else Y[:, 0]
+
+
+def pillbox(n, radius=0.4, length=0.8, origin=-0.5, size=1.0):
+    """example/pillbox.py:14-17 -- Cylinder(R, axis z) ∩ Slab(thickness, normal z) in a box."""
+    cyl = Shape.cylinder(radius, (0, 0, 1), (0, 0, 0))
+    caps = Shape.slab(length, (0, 0, 1), (0, 0, 0))
+    cav = Shape.intersection([cyl, caps])
+    return Sim(n, origin=(origin,) * 3, size=(size,) * 3, pec=cav)
+
+
+def vacuum(n, phase_shifts=None, literal=False):
+    """example/vacuum.py:7-22 -- periodic unit box, no PEC."""
+    return Sim(n, origin=(0.0,) * 3, size=(1.0,) * 3, phase_shifts=phase_shifts, literal_upper_periodic_e=literal)
