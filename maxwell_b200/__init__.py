@@ -1,0 +1,447 @@
+"""maxwell_b200 -- B200-native eigensolve inner loop for bauerca/maxwell.
+
+The product is libmxgpu.so (hand-written sm_100a CUDA behind the C ABI in include/mxgpu.h)
+plus the C++ shim classes in include/mx/. This Python module is only a ctypes veneer with the
+reference's class and method names (MxMap, MxMultiVector / MxAnasaziMV, MxCrsMatrix) so tests
+and bench.py read like the reference's own call sites. It never falls back to a CPU path: if
+the library is missing or no GPU is present, construction fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+MAX_COLS = 128
+LAYOUT_DICT, LAYOUT_SELL = 0, 1
+
+
+class MxError(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(_HERE, "libmxgpu.so")
+
+
+def load_library():
+    """dlopen libmxgpu.so and declare every entry point of include/mxgpu.h."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise MxError("libmxgpu.so not built (run `python __graft_entry__.py`); there is no CPU fallback")
+    L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    vp, i64, i32, dp = C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double)
+    pvp = C.POINTER(vp)
+    ip = C.POINTER(C.c_int)
+    sig = {
+        "mxg_last_error": (C.c_char_p, []),
+        "mxg_version": (i32, []),
+        "mxg_ctx_create": (i32, [i32, pvp]),
+        "mxg_ctx_destroy": (i32, [vp]),
+        "mxg_ctx_sync": (i32, [vp]),
+        "mxg_ctx_rank": (i32, [vp]),
+        "mxg_ctx_num_ranks": (i32, [vp]),
+        "mxg_comm_unique_id": (i32, [vp]),
+        "mxg_ctx_comm_init": (i32, [vp, i32, i32, vp]),
+        "mxg_ctx_stream": (vp, [vp]),
+        "mxg_ctx_launch_count": (i64, [vp]),
+        "mxg_ctx_event_record": (i32, [vp, i32]),
+        "mxg_ctx_event_elapsed_ms": (i32, [vp, i32, i32, dp]),
+        "mxg_host_alloc": (vp, [C.c_size_t]),
+        "mxg_host_free": (None, [vp]),
+        "mxg_crs_apply_timed": (i32, [vp, vp, vp, dp]),
+        "mxg_map_create": (i32, [vp, i64, vp, i64, pvp]),
+        "mxg_map_destroy": (i32, [vp]),
+        "mxg_map_local_size": (i64, [vp]),
+        "mxg_map_global_size": (i64, [vp]),
+        "mxg_mv_create": (i32, [vp, i32, i32, pvp]),
+        "mxg_mv_clone_copy": (i32, [vp, ip, i32, pvp]),
+        "mxg_mv_view": (i32, [vp, ip, i32, pvp]),
+        "mxg_mv_destroy": (i32, [vp]),
+        "mxg_mv_num_cols": (i32, [vp]),
+        "mxg_mv_local_length": (i64, [vp]),
+        "mxg_mv_global_length": (i64, [vp]),
+        "mxg_mv_is_complex": (i32, [vp]),
+        "mxg_mv_set_block": (i32, [vp, vp, ip, i32]),
+        "mxg_mv_assign": (i32, [vp, vp]),
+        "mxg_mv_fill": (i32, [vp, dp]),
+        "mxg_mv_random": (i32, [vp, C.c_uint64]),
+        "mxg_mv_scale": (i32, [vp, dp]),
+        "mxg_mv_scale_cols": (i32, [vp, vp]),
+        "mxg_mv_conj": (i32, [vp]),
+        "mxg_mv_update": (i32, [vp, dp, vp, dp]),
+        "mxg_mv_add_mv": (i32, [vp, dp, vp, dp, vp]),
+        "mxg_mv_norm2": (i32, [vp, vp]),
+        "mxg_mv_dot": (i32, [vp, vp, vp]),
+        "mxg_mv_normalize": (i32, [vp]),
+        "mxg_mv_trans_mv": (i32, [dp, vp, vp, vp, i32]),
+        "mxg_mv_times_mat_add_mv": (i32, [dp, vp, vp, i32, dp, vp]),
+        "mxg_mv_upload": (i32, [vp, vp, i64]),
+        "mxg_mv_download": (i32, [vp, vp, i64]),
+        "mxg_mv_col_ptr": (vp, [vp, i32]),
+        "mxg_crs_create": (i32, [vp, vp, vp, vp, vp, i32, pvp]),
+        "mxg_crs_create_opts": (i32, [vp, vp, vp, vp, vp, i32, i32, pvp]),
+        "mxg_crs_destroy": (i32, [vp]),
+        "mxg_crs_apply": (i32, [vp, vp, vp]),
+        "mxg_crs_apply_axpby": (i32, [vp, dp, vp, dp, vp]),
+        "mxg_crs_stats": (i32, [vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = L
+    return L
+
+
+EXPORTED_SYMBOLS = None  # filled lazily by exported_symbols()
+
+
+def _ck(rc):
+    if rc != 0:
+        raise MxError(load_library().mxg_last_error().decode())
+
+
+def _scalar(a):
+    a = complex(a)
+    return (C.c_double * 2)(a.real, a.imag)
+
+
+def _ints(v):
+    v = [int(x) for x in v]
+    return (C.c_int * len(v))(*v), len(v)
+
+
+class Context:
+    """One GPU + its streams (+ NCCL communicator): the MxComm of the B200 path (MxComm.hpp:14-37)."""
+
+    def __init__(self, device=0):
+        self._L = load_library()
+        h = C.c_void_p()
+        _ck(self._L.mxg_ctx_create(int(device), C.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * 128)()
+        _ck(load_library().mxg_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, rank, nranks, unique_id=None):
+        buf = (C.c_ubyte * 128)(*unique_id) if unique_id is not None else None
+        _ck(self._L.mxg_ctx_comm_init(self.h, rank, nranks, buf))
+
+    def myPID(self):
+        return self._L.mxg_ctx_rank(self.h)
+
+    def numProc(self):
+        return self._L.mxg_ctx_num_ranks(self.h)
+
+    def sync(self):
+        _ck(self._L.mxg_ctx_sync(self.h))
+
+    def stream(self):
+        return self._L.mxg_ctx_stream(self.h)
+
+    def launch_count(self):
+        return self._L.mxg_ctx_launch_count(self.h)
+
+    def event_record(self, slot):
+        _ck(self._L.mxg_ctx_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_double()
+        _ck(self._L.mxg_ctx_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self.h:
+            self._L.mxg_ctx_destroy(self.h)
+            self.h = None
+
+
+class MxMap:
+    """MxMap(globalIndices, comm) (MxMap.hpp:22-103): this rank's owned GIDs, ascending."""
+
+    def __init__(self, ctx, num_global, my_gids):
+        self.ctx = ctx
+        self._L = ctx._L
+        g = np.ascontiguousarray(my_gids, dtype=np.int64)
+        h = C.c_void_p()
+        _ck(self._L.mxg_map_create(ctx.h, int(num_global), g.ctypes.data, len(g), C.byref(h)))
+        self.h = h
+        self.gids = g
+
+    def getNodeNumIndices(self):
+        return self._L.mxg_map_local_size(self.h)
+
+    def getGlobalNumIndices(self):
+        return self._L.mxg_map_global_size(self.h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self._L.mxg_map_destroy(self.h)
+        except Exception:
+            pass
+
+
+class MxMultiVector:
+    """MxMultiVector / MxAnasaziMV (MxMultiVector.hpp:16-89, MxAnasaziMV.hpp:23-136)."""
+
+    def __init__(self, map_, num_vecs, is_complex=False, _handle=None):
+        self.map = map_
+        self._L = map_._L
+        if _handle is None:
+            h = C.c_void_p()
+            _ck(self._L.mxg_mv_create(map_.h, int(num_vecs), int(bool(is_complex)), C.byref(h)))
+            _handle = h
+        self.h = _handle
+        self.is_complex = bool(self._L.mxg_mv_is_complex(self.h))
+        self.dtype = np.complex128 if self.is_complex else np.float64
+
+    # -- Anasazi::MultiVec surface -------------------------------------------------------
+    def Clone(self, num_vecs):
+        return MxMultiVector(self.map, num_vecs, self.is_complex)
+
+    def CloneCopy(self, index=None):
+        h = C.c_void_p()
+        if index is None:
+            _ck(self._L.mxg_mv_clone_copy(self.h, None, 0, C.byref(h)))
+        else:
+            arr, n = _ints(index)
+            _ck(self._L.mxg_mv_clone_copy(self.h, arr, n, C.byref(h)))
+        return MxMultiVector(self.map, 0, _handle=h)
+
+    def CloneView(self, index):
+        arr, n = _ints(index)
+        h = C.c_void_p()
+        _ck(self._L.mxg_mv_view(self.h, arr, n, C.byref(h)))
+        return MxMultiVector(self.map, 0, _handle=h)
+
+    CloneViewNonConst = CloneView
+
+    def GetVecLength(self):
+        return self._L.mxg_mv_global_length(self.h)
+
+    def GetNumberVecs(self):
+        return self._L.mxg_mv_num_cols(self.h)
+
+    getNumVecs = GetNumberVecs
+
+    def getLocalLength(self):
+        return self._L.mxg_mv_local_length(self.h)
+
+    def MvTimesMatAddMv(self, alpha, A, B, beta):
+        """this = alpha*A*B + beta*this; B: host (k x b) array."""
+        Bh = np.asfortranarray(np.asarray(B, dtype=self.dtype).reshape(A.GetNumberVecs(), -1))
+        _ck(self._L.mxg_mv_times_mat_add_mv(_scalar(alpha), A.h, Bh.ctypes.data, Bh.shape[0], _scalar(beta), self.h))
+
+    def MvAddMv(self, alpha, A, beta, B):
+        _ck(self._L.mxg_mv_add_mv(self.h, _scalar(alpha), A.h, _scalar(beta), B.h))
+
+    def MvTransMv(self, alpha, A):
+        """returns alpha * A^H * this as a host (k x b) array."""
+        k, b = A.GetNumberVecs(), self.GetNumberVecs()
+        out = np.zeros((k, b), dtype=self.dtype, order="F")
+        _ck(self._L.mxg_mv_trans_mv(_scalar(alpha), A.h, self.h, out.ctypes.data, k))
+        return out
+
+    def trans_mv(self, alpha, X):
+        """alpha * this^H * X."""
+        return X.MvTransMv(alpha, self)
+
+    def MvDot(self, A):
+        out = np.zeros(self.GetNumberVecs(), dtype=self.dtype)
+        _ck(self._L.mxg_mv_dot(A.h, self.h, out.ctypes.data))
+        return out
+
+    def dot(self, mv):
+        """mv^dagger . this (MxMultiVector.hpp:58-61)."""
+        return self.MvDot(mv)
+
+    def MvNorm(self):
+        out = np.zeros(self.GetNumberVecs(), dtype=np.float64)
+        _ck(self._L.mxg_mv_norm2(self.h, out.ctypes.data))
+        return out
+
+    norm2 = MvNorm
+
+    def SetBlock(self, A, index):
+        arr, n = _ints(index)
+        _ck(self._L.mxg_mv_set_block(self.h, A.h, arr, n))
+
+    def MvScale(self, alpha):
+        if np.ndim(alpha) == 0:
+            _ck(self._L.mxg_mv_scale(self.h, _scalar(alpha)))
+        else:
+            a = np.ascontiguousarray(alpha, dtype=self.dtype)
+            assert len(a) == self.GetNumberVecs()
+            _ck(self._L.mxg_mv_scale_cols(self.h, a.ctypes.data))
+
+    scale = MvScale
+
+    def MvRandom(self, seed=12345):
+        _ck(self._L.mxg_mv_random(self.h, int(seed)))
+
+    random = MvRandom
+
+    def MvInit(self, alpha):
+        _ck(self._L.mxg_mv_fill(self.h, _scalar(alpha)))
+
+    set = MvInit
+
+    def conj(self):
+        _ck(self._L.mxg_mv_conj(self.h))
+
+    def update(self, a, A, s):
+        _ck(self._L.mxg_mv_update(self.h, _scalar(a), A.h, _scalar(s)))
+
+    def assign(self, src):
+        _ck(self._L.mxg_mv_assign(self.h, src.h))
+
+    def normalize(self):
+        _ck(self._L.mxg_mv_normalize(self.h))
+
+    # -- host transfers -------------------------------------------------------------------
+    def from_host(self, arr):
+        n, b = self.getLocalLength(), self.GetNumberVecs()
+        a = np.asfortranarray(np.asarray(arr, dtype=self.dtype).reshape(n, b))
+        _ck(self._L.mxg_mv_upload(self.h, a.ctypes.data, n))
+
+    def to_host(self, out=None):
+        n, b = self.getLocalLength(), self.GetNumberVecs()
+        if out is None:
+            out = np.empty((n, b), dtype=self.dtype, order="F")
+        _ck(self._L.mxg_mv_download(self.h, out.ctypes.data, n))
+        return out
+
+    def col_ptr(self, j):
+        return self._L.mxg_mv_col_ptr(self.h, j)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self._L.mxg_mv_destroy(self.h)
+        except Exception:
+            pass
+
+
+MxAnasaziMV = MxMultiVector
+
+
+class MxCrsMatrix:
+    """MxCrsMatrix (MxCrsMatrix.hpp:14-82): host assembly by insertRowValues, device apply."""
+
+    def __init__(self, row_map, col_map=None, is_complex=False):
+        self.row_map = row_map
+        self.col_map = col_map if col_map is not None else row_map
+        self.is_complex = bool(is_complex)
+        self._L = row_map._L
+        self._rows = {}
+        self.h = None
+
+    def insertRowValues(self, row, cols, vals):
+        """Global indices, as in the reference (MxCrsMatrix.hpp:31-36); duplicates are summed."""
+        self._rows.setdefault(int(row), []).extend(zip([int(c) for c in cols], list(vals)))
+
+    def fillComplete(self, domain_map=None, range_map=None, layout=None):
+        if domain_map is not None:
+            self.col_map = domain_map
+        gids = self.row_map.gids
+        rowptr = np.zeros(len(gids) + 1, dtype=np.int64)
+        cols, vals = [], []
+        for i, g in enumerate(gids):
+            ent = self._rows.get(int(g), [])
+            cols.extend(c for c, _ in ent)
+            vals.extend(v for _, v in ent)
+            rowptr[i + 1] = len(cols)
+        self._finish(rowptr, np.asarray(cols, dtype=np.int64),
+                     np.asarray(vals, dtype=np.complex128 if self.is_complex else np.float64), layout)
+        self._rows = {}
+
+    @classmethod
+    def from_csr(cls, row_map, domain_map, rowptr, col_gids, vals, layout=None):
+        A = cls(row_map, domain_map, np.iscomplexobj(vals))
+        A._finish(np.ascontiguousarray(rowptr, dtype=np.int64), np.ascontiguousarray(col_gids, dtype=np.int64),
+                  np.ascontiguousarray(vals, dtype=np.complex128 if A.is_complex else np.float64), layout)
+        return A
+
+    def _finish(self, rowptr, cols, vals, layout):
+        h = C.c_void_p()
+        if layout is None:
+            _ck(self._L.mxg_crs_create(self.row_map.h, self.col_map.h, rowptr.ctypes.data, cols.ctypes.data,
+                                       vals.ctypes.data, int(self.is_complex), C.byref(h)))
+        else:
+            _ck(self._L.mxg_crs_create_opts(self.row_map.h, self.col_map.h, rowptr.ctypes.data, cols.ctypes.data,
+                                            vals.ctypes.data, int(self.is_complex), int(layout), C.byref(h)))
+        self.h = h
+
+    def isFilled(self):
+        return self.h is not None
+
+    def getDomainMap(self):
+        return self.col_map
+
+    def getRangeMap(self):
+        return self.row_map
+
+    def apply(self, x, y):
+        _ck(self._L.mxg_crs_apply(self.h, x.h, y.h))
+
+    def apply_axpby(self, alpha, x, beta, y):
+        _ck(self._L.mxg_crs_apply_axpby(self.h, _scalar(alpha), x.h, _scalar(beta), y.h))
+
+    def apply_timed(self, x, y):
+        ms = (C.c_double * 4)()
+        _ck(self._L.mxg_crs_apply_timed(self.h, x.h, y.h, ms))
+        return {"dict_ms": ms[0], "sell_ms": ms[1], "pre_ms": ms[2], "total_ms": ms[3]}
+
+    def stats(self):
+        out = (C.c_int64 * 8)()
+        _ck(self._L.mxg_crs_stats(self.h, out))
+        keys = ["rows", "nnz", "dict_rows", "patterns", "device_bytes", "ghosts", "ghost_rows", "ell_entries"]
+        return dict(zip(keys, list(out)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self._L.mxg_crs_destroy(self.h)
+        except Exception:
+            pass
+
+
+def pinned_array(shape, dtype=np.float64):
+    """numpy array backed by cudaMallocHost memory (freed when the array is collected)."""
+    L = load_library()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = L.mxg_host_alloc(n)
+    if not p:
+        raise MxError(L.mxg_last_error().decode())
+    buf = (C.c_ubyte * n).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape, order="F")
+    _PINNED[id(buf)] = (buf, p)
+    return arr
+
+
+_PINNED = {}
+
+
+def hash_uniform(seed, gids, col, part=0):
+    """Host mirror of the counter-based generator behind MvRandom (mxg_mvops.cu: hashUniform)."""
+    with np.errstate(over="ignore"):
+        g = np.asarray(gids, dtype=np.uint64)
+        z = (np.uint64(seed) ^ (g * np.uint64(0x9E3779B97F4A7C15))
+             ^ np.uint64(((col + 1) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF)
+             ^ np.uint64((part * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF))
+        z ^= z >> np.uint64(30)
+        z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27)
+        z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+        return 2.0 * ((z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)) - 1.0

@@ -1,0 +1,148 @@
+// Internal declarations shared by the libmxgpu translation units. sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "mxgpu.h"
+
+namespace mxg {
+
+void setError(const char* fmt, ...);
+
+#define MXG_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      mxg::setError("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+      return MXG_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+#define MXG_NCCL(expr)                                                                       \
+  do {                                                                                       \
+    ncclResult_t r_ = (expr);                                                                \
+    if (r_ != ncclSuccess) {                                                                 \
+      mxg::setError("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, ncclGetErrorString(r_)); \
+      return MXG_ERR_NCCL;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+#define MXG_REQUIRE(cond, ...)      \
+  do {                              \
+    if (!(cond)) {                  \
+      mxg::setError(__VA_ARGS__);   \
+      return MXG_ERR_ARG;           \
+    }                               \
+  } while (0)
+
+// complex128 on the device: plain (re, im) pair, bit-compatible with std::complex<double>
+struct __align__(16) zd {
+  double x, y;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ double ldgT(const double* p) { return __ldg(p); }
+__device__ __forceinline__ zd ldgT(const zd* p) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return {v.x, v.y};
+}
+#endif
+__host__ __device__ inline zd operator+(zd a, zd b) { return {a.x + b.x, a.y + b.y}; }
+__host__ __device__ inline zd operator-(zd a, zd b) { return {a.x - b.x, a.y - b.y}; }
+__host__ __device__ inline zd operator*(zd a, zd b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__host__ __device__ inline zd conjz(zd a) { return {a.x, -a.y}; }
+__host__ __device__ inline double conjz(double a) { return a; }
+__host__ __device__ inline zd& operator+=(zd& a, zd b) { a.x += b.x; a.y += b.y; return a; }
+__host__ __device__ inline void fmaInto(double& acc, double a, double b) { acc = fma(a, b, acc); }
+__host__ __device__ inline void fmaInto(zd& acc, zd a, zd b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+template <class T> __host__ __device__ inline T zeroOf();
+template <> __host__ __device__ inline double zeroOf<double>() { return 0.0; }
+template <> __host__ __device__ inline zd zeroOf<zd>() { return {0.0, 0.0}; }
+template <class T> __host__ __device__ inline T scalarOf(const double s[2]);
+template <> __host__ __device__ inline double scalarOf<double>(const double s[2]) { return s[0]; }
+template <> __host__ __device__ inline zd scalarOf<zd>(const double s[2]) { return {s[0], s[1]}; }
+__host__ __device__ inline bool isZero(double a) { return a == 0.0; }
+__host__ __device__ inline bool isZero(zd a) { return a.x == 0.0 && a.y == 0.0; }
+__host__ __device__ inline bool isOne(double a) { return a == 1.0; }
+__host__ __device__ inline bool isOne(zd a) { return a.x == 1.0 && a.y == 0.0; }
+
+// Column pointer table passed by value to kernels: views with arbitrary column lists cost
+// nothing extra (MxMultiVector.cpp:29-44 semantics).
+template <class T>
+struct ColTable {
+  T* p[MXG_MAX_COLS];
+};
+
+}  // namespace mxg
+
+struct mxg_ctx {
+  int device = 0;
+  int numSMs = 148;
+  cudaStream_t stream = nullptr;       // compute stream
+  cudaStream_t commStream = nullptr;   // halo exchange stream
+  cudaEvent_t evA = nullptr, evB = nullptr;
+  cudaEvent_t timer[16] = {};          // user timing slots (created lazily)
+  cudaEvent_t prof[6] = {};            // per-kernel profiling events
+  bool profiling = false;
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  double* dScratch = nullptr;          // reduction partials / small device results
+  size_t scratchBytes = 0;
+  double* hPinned = nullptr;           // pinned host staging for small results and dense B
+  size_t pinnedBytes = 0;
+  int64_t launches = 0;
+};
+
+struct mxg_map {
+  mxg_ctx* ctx = nullptr;
+  int64_t nGlobal = 0, nLocal = 0;
+  std::vector<int64_t> gids;           // host copy (ascending)
+  int64_t* dGids = nullptr;            // device copy (RNG keys, halo plans)
+  int refs = 1;
+};
+
+struct MvStorage {
+  mxg_ctx* ctx = nullptr;
+  void* base = nullptr;
+  size_t bytes = 0;
+  ~MvStorage();
+};
+
+struct mxg_mv {
+  mxg_map* map = nullptr;
+  bool isComplex = false;
+  int ncols = 0;
+  int64_t ld = 0;                          // local length (scalars per column)
+  std::shared_ptr<MvStorage> storage;      // shared with views
+  std::vector<void*> col;                  // device pointer of each column
+  std::vector<int> baseCol;                // column position in the underlying allocation
+};
+
+namespace mxg {
+template <class T>
+inline ColTable<T> tableOf(const mxg_mv* mv, int first = 0, int count = -1) {
+  ColTable<T> t;
+  if (count < 0) count = mv->ncols - first;
+  for (int j = 0; j < count; ++j) t.p[j] = static_cast<T*>(mv->col[first + j]);
+  return t;
+}
+int ensureScratch(mxg_ctx* ctx, size_t bytes);
+int ensurePinned(mxg_ctx* ctx, size_t bytes);
+// sum `count` doubles in ctx->dScratch over all ranks (no-op on one rank)
+int allReduceScratch(mxg_ctx* ctx, size_t count);
+inline int gridFor(const mxg_ctx* ctx, int64_t work, int block, int perSM) {
+  int64_t need = (work + block - 1) / block;
+  int64_t cap = int64_t(ctx->numSMs) * perSM;
+  if (need < 1) need = 1;
+  return int(need < cap ? need : cap);
+}
+}  // namespace mxg

@@ -1,0 +1,524 @@
+// libmxgpu: multivector block operations (K5-K14 of SURVEY.md section 2.3). All kernels are
+// HBM-bound streaming or reduction kernels; grids are sized in multiples of the SM count.
+#include <cmath>
+#include <cstring>
+
+#include "mxg_internal.h"
+
+using namespace mxg;
+
+namespace {
+
+constexpr int kBlock = 256;
+
+template <class T>
+struct ScalarList {
+  T v[MXG_MAX_COLS];
+};
+
+// ---- elementwise -------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_fill(ColTable<T> t, int64_t n, T alpha) {
+  T* __restrict__ c = t.p[blockIdx.y];
+  for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) c[i] = alpha;
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_scale_cols(ColTable<T> t, int64_t n, ScalarList<T> a) {
+  T* __restrict__ c = t.p[blockIdx.y];
+  const T s = a.v[blockIdx.y];
+  for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) c[i] = s * c[i];
+}
+
+__global__ void __launch_bounds__(kBlock) k_conj(ColTable<zd> t, int64_t n) {
+  zd* __restrict__ c = t.p[blockIdx.y];
+  for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) c[i].y = -c[i].y;
+}
+
+// dst = a*A + b*B. Pure elementwise, so A or B may alias dst. A zero coefficient drops its
+// operand entirely (Epetra_MultiVector::Update semantics).
+template <class T, bool USE_A, bool USE_B>
+__global__ void __launch_bounds__(kBlock) k_axpby(ColTable<T> d, T a, ColTable<T> A, T b, ColTable<T> B, int64_t n) {
+  T* dst = d.p[blockIdx.y];
+  const T* pa = A.p[blockIdx.y];
+  const T* pb = B.p[blockIdx.y];
+  for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) {
+    T r = zeroOf<T>();
+    if (USE_A) r = a * pa[i];
+    if (USE_B) { T tb = b * pb[i]; r = USE_A ? r + tb : tb; }
+    dst[i] = r;
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_copy(ColTable<T> d, ColTable<T> s, int64_t n) {
+  T* __restrict__ dst = d.p[blockIdx.y];
+  const T* __restrict__ src = s.p[blockIdx.y];
+  for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) dst[i] = src[i];
+}
+
+// Counter-based generator: uniform (-1,1) from a hash of (seed, global DOF id, column, re/im).
+__host__ __device__ inline double hashUniform(uint64_t seed, uint64_t gid, uint64_t col, uint64_t part) {
+  uint64_t z = seed ^ (gid * 0x9E3779B97F4A7C15ull) ^ ((col + 1) * 0xBF58476D1CE4E5B9ull) ^ (part * 0x94D049BB133111EBull);
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return 2.0 * (double(z >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
+}
+struct ColIds {
+  int v[MXG_MAX_COLS];
+};
+__global__ void __launch_bounds__(kBlock) k_random_real(ColTable<double> t, ColIds ids, const int64_t* __restrict__ gids, int64_t n, uint64_t seed) {
+  double* __restrict__ c = t.p[blockIdx.y];
+  const uint64_t col = ids.v[blockIdx.y];
+  for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock)
+    c[i] = hashUniform(seed, uint64_t(gids[i]), col, 0);
+}
+__global__ void __launch_bounds__(kBlock) k_random_cplx(ColTable<zd> t, ColIds ids, const int64_t* __restrict__ gids, int64_t n, uint64_t seed) {
+  zd* __restrict__ c = t.p[blockIdx.y];
+  const uint64_t col = ids.v[blockIdx.y];
+  for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock)
+    c[i] = {hashUniform(seed, uint64_t(gids[i]), col, 0), hashUniform(seed, uint64_t(gids[i]), col, 1)};
+}
+
+// ---- reductions --------------------------------------------------------------------------
+__device__ inline double warpSum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ inline zd warpSum(zd v) { return {warpSum(v.x), warpSum(v.y)}; }
+
+template <class T>
+__device__ inline T blockSum(T v, T* sm /* kBlock/32 entries */) {
+  v = warpSum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sm[w] = v;
+  __syncthreads();
+  T r = zeroOf<T>();
+  if (w == 0) {
+    r = l < kBlock / 32 ? sm[l] : zeroOf<T>();
+    r = warpSum(r);
+  }
+  return r;  // valid in warp 0
+}
+
+// partial[col * gridDim.x + block] = sum over this block's rows of conj(a) * b
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_dot_partial(ColTable<T> A, ColTable<T> B, int64_t n, T* __restrict__ partial) {
+  __shared__ T sm[kBlock / 32];
+  const T* __restrict__ a = A.p[blockIdx.y];
+  const T* __restrict__ b = B.p[blockIdx.y];
+  T acc0 = zeroOf<T>(), acc1 = zeroOf<T>();
+  const int64_t stride = int64_t(gridDim.x) * kBlock;
+  int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x;
+  for (; i + stride < n; i += 2 * stride) {
+    fmaInto(acc0, conjz(a[i]), b[i]);
+    fmaInto(acc1, conjz(a[i + stride]), b[i + stride]);
+  }
+  if (i < n) fmaInto(acc0, conjz(a[i]), b[i]);
+  T r = blockSum(acc0 + acc1, sm);
+  if (threadIdx.x == 0) partial[blockIdx.y * int64_t(gridDim.x) + blockIdx.x] = r;
+}
+
+// out[item] = sum_{p < np} partial[item * np + p], fixed order -> deterministic
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_reduce_partials(const T* __restrict__ partial, int np, T* __restrict__ out) {
+  __shared__ T sm[kBlock / 32];
+  T acc = zeroOf<T>();
+  for (int p = threadIdx.x; p < np; p += kBlock) acc += partial[blockIdx.x * int64_t(np) + p];
+  T r = blockSum(acc, sm);
+  if (threadIdx.x == 0) out[blockIdx.x] = r;
+}
+
+// ---- tall-skinny Gram product: C(k x b) = A^H X ---------------------------------------------
+// Each thread owns a KT x BT register tile of C and streams rows with stride kBlock (coalesced
+// per column). blockIdx.x enumerates tiles (fastest), blockIdx.y row slices: blocks that share
+// rows are co-scheduled so the re-read of A/X columns by other tiles is served from L2.
+template <class T, int KT, int BT>
+__global__ void __launch_bounds__(kBlock) k_trans_mv(ColTable<T> A, int k, ColTable<T> X, int b, int64_t n,
+                                                     int tilesB, T* __restrict__ partial /* [gridDim.y][k*b] */) {
+  __shared__ T sm[kBlock / 32];
+  const int tk = blockIdx.x / tilesB, tb = blockIdx.x % tilesB;
+  const int k0 = tk * KT, b0 = tb * BT;
+  const T* pa[KT];
+  const T* px[BT];
+#pragma unroll
+  for (int i = 0; i < KT; ++i) pa[i] = A.p[min(k0 + i, k - 1)];
+#pragma unroll
+  for (int j = 0; j < BT; ++j) px[j] = X.p[min(b0 + j, b - 1)];
+  T acc[KT][BT];
+#pragma unroll
+  for (int i = 0; i < KT; ++i)
+#pragma unroll
+    for (int j = 0; j < BT; ++j) acc[i][j] = zeroOf<T>();
+  for (int64_t r = blockIdx.y * int64_t(kBlock) + threadIdx.x; r < n; r += int64_t(gridDim.y) * kBlock) {
+    T av[KT], xv[BT];
+#pragma unroll
+    for (int i = 0; i < KT; ++i) av[i] = conjz(pa[i][r]);
+#pragma unroll
+    for (int j = 0; j < BT; ++j) xv[j] = px[j][r];
+#pragma unroll
+    for (int i = 0; i < KT; ++i)
+#pragma unroll
+      for (int j = 0; j < BT; ++j) fmaInto(acc[i][j], av[i], xv[j]);
+  }
+#pragma unroll
+  for (int i = 0; i < KT; ++i)
+#pragma unroll
+    for (int j = 0; j < BT; ++j) {
+      T r = blockSum(acc[i][j], sm);
+      if (threadIdx.x == 0 && k0 + i < k && b0 + j < b)
+        partial[(int64_t(k0 + i) + int64_t(b0 + j) * k) * gridDim.y + blockIdx.y] = r;
+    }
+}
+
+// ---- tall-skinny update: Y = alpha * A * B + beta * Y ---------------------------------------
+// The small dense B rides in the kernel parameter block (constant bank): the FMAs take it as a
+// uniform operand, so the only memory instructions are the streaming loads of A and Y.
+constexpr int kMaxBParam = 1536;  // doubles (12 KB of the 32 KB parameter space)
+struct DenseParam {
+  double v[kMaxBParam];
+};
+__device__ inline double denseAt(const DenseParam& B, int idx, double) { return B.v[idx]; }
+__device__ inline zd denseAt(const DenseParam& B, int idx, zd) { return {B.v[2 * idx], B.v[2 * idx + 1]}; }
+
+template <class T, int BT>
+__global__ void __launch_bounds__(kBlock) k_times_mat(ColTable<T> A, int k, const __grid_constant__ DenseParam B, int b0, int bcount,
+                                                      T alpha, T beta, bool useY, ColTable<T> Y, int64_t n) {
+  for (int64_t r = blockIdx.x * int64_t(kBlock) + threadIdx.x; r < n; r += int64_t(gridDim.x) * kBlock) {
+    T acc[BT];
+#pragma unroll
+    for (int j = 0; j < BT; ++j) acc[j] = zeroOf<T>();
+    for (int i = 0; i < k; ++i) {
+      const T a = A.p[i][r];
+#pragma unroll
+      for (int j = 0; j < BT; ++j)
+        if (j < bcount) fmaInto(acc[j], a, denseAt(B, i + (b0 + j) * k, T()));
+    }
+#pragma unroll
+    for (int j = 0; j < BT; ++j)
+      if (j < bcount) {
+        T* y = Y.p[b0 + j];
+        T v = alpha * acc[j];
+        if (useY) v = v + beta * y[r];
+        y[r] = v;
+      }
+  }
+}
+
+template <class T>
+dim3 gridCols(const mxg_ctx* ctx, int64_t n, int ncols) {
+  int perCol = gridFor(ctx, n, kBlock * 4, 8);
+  int cap = (ctx->numSMs * 8 + ncols - 1) / ncols;
+  if (perCol > cap) perCol = cap;
+  if (perCol < 1) perCol = 1;
+  return dim3(perCol, ncols);
+}
+
+#define LAUNCH_CHECK(ctx)                   \
+  do {                                      \
+    (ctx)->launches++;                      \
+    MXG_CUDA(cudaGetLastError());           \
+  } while (0)
+
+template <class T>
+int fillImpl(mxg_mv* mv, const double alpha[2]) {
+  mxg_ctx* ctx = mv->map->ctx;
+  if (mv->ld == 0) return MXG_OK;
+  k_fill<T><<<gridCols<T>(ctx, mv->ld, mv->ncols), kBlock, 0, ctx->stream>>>(tableOf<T>(mv), mv->ld, scalarOf<T>(alpha));
+  LAUNCH_CHECK(ctx);
+  return MXG_OK;
+}
+
+template <class T>
+int scaleColsImpl(mxg_mv* mv, const double* alphas, bool same) {
+  mxg_ctx* ctx = mv->map->ctx;
+  if (mv->ld == 0) return MXG_OK;
+  ScalarList<T> a;
+  constexpr int w = sizeof(T) / sizeof(double);
+  for (int j = 0; j < mv->ncols; ++j) {
+    double s[2] = {alphas[same ? 0 : j * w], w == 2 ? alphas[same ? 1 : j * w + 1] : 0.0};
+    a.v[j] = scalarOf<T>(s);
+  }
+  k_scale_cols<T><<<gridCols<T>(ctx, mv->ld, mv->ncols), kBlock, 0, ctx->stream>>>(tableOf<T>(mv), mv->ld, a);
+  LAUNCH_CHECK(ctx);
+  return MXG_OK;
+}
+
+template <class T>
+int axpbyImpl(mxg_mv* dst, const double alpha[2], const mxg_mv* A, const double beta[2], const mxg_mv* B) {
+  mxg_ctx* ctx = dst->map->ctx;
+  if (dst->ld == 0) return MXG_OK;
+  const T a = scalarOf<T>(alpha), b = scalarOf<T>(beta);
+  const bool ua = !isZero(a), ub = !isZero(b);
+  const dim3 grid = gridCols<T>(ctx, dst->ld, dst->ncols);
+  auto d = tableOf<T>(dst), ta = tableOf<T>(A), tb = tableOf<T>(B);
+  if (ua && ub) k_axpby<T, true, true><<<grid, kBlock, 0, ctx->stream>>>(d, a, ta, b, tb, dst->ld);
+  else if (ua) k_axpby<T, true, false><<<grid, kBlock, 0, ctx->stream>>>(d, a, ta, b, tb, dst->ld);
+  else if (ub) k_axpby<T, false, true><<<grid, kBlock, 0, ctx->stream>>>(d, a, ta, b, tb, dst->ld);
+  else k_axpby<T, false, false><<<grid, kBlock, 0, ctx->stream>>>(d, a, ta, b, tb, dst->ld);
+  LAUNCH_CHECK(ctx);
+  return MXG_OK;
+}
+
+// column-wise conj(a_j).b_j into ctx->dScratch[0 .. ncols*w), all-reduced; leaves the result on the device
+template <class T>
+int dotToScratch(const mxg_mv* a, const mxg_mv* b) {
+  mxg_ctx* ctx = a->map->ctx;
+  const int nc = a->ncols;
+  constexpr int w = sizeof(T) / sizeof(double);
+  int np = gridFor(ctx, a->ld, kBlock * 8, 4);
+  int cap = (ctx->numSMs * 4 + nc - 1) / nc;
+  if (np > cap) np = cap;
+  if (np < 1) np = 1;
+  int rc = ensureScratch(ctx, sizeof(T) * (size_t(nc) * np + nc));
+  if (rc) return rc;
+  T* out = reinterpret_cast<T*>(ctx->dScratch);
+  T* partial = out + nc;
+  k_dot_partial<T><<<dim3(np, nc), kBlock, 0, ctx->stream>>>(tableOf<T>(a), tableOf<T>(b), a->ld, partial);
+  LAUNCH_CHECK(ctx);
+  k_reduce_partials<T><<<nc, kBlock, 0, ctx->stream>>>(partial, np, out);
+  LAUNCH_CHECK(ctx);
+  return allReduceScratch(ctx, size_t(nc) * w);
+}
+
+int fetchScratch(mxg_ctx* ctx, double* host, size_t count) {
+  int rc = ensurePinned(ctx, count * sizeof(double));
+  if (rc) return rc;
+  MXG_CUDA(cudaMemcpyAsync(ctx->hPinned, ctx->dScratch, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  MXG_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(host, ctx->hPinned, count * sizeof(double));
+  return MXG_OK;
+}
+
+template <class T>
+int transMvImpl(const double alpha[2], const mxg_mv* A, const mxg_mv* X, double* B, int ldb) {
+  mxg_ctx* ctx = A->map->ctx;
+  constexpr int w = sizeof(T) / sizeof(double);
+  constexpr int KT = (w == 1) ? 8 : 4, BT = 4;
+  const int k = A->ncols, b = X->ncols;
+  const int tilesK = (k + KT - 1) / KT, tilesB = (b + BT - 1) / BT;
+  const int tiles = tilesK * tilesB;
+  int slices = (ctx->numSMs * 4 + tiles - 1) / tiles;
+  int maxSlices = int((A->ld + kBlock - 1) / kBlock);
+  if (slices > maxSlices) slices = maxSlices;
+  if (slices < 1) slices = 1;
+  const size_t kb = size_t(k) * b;
+  int rc = ensureScratch(ctx, sizeof(T) * (kb * slices + kb));
+  if (rc) return rc;
+  T* out = reinterpret_cast<T*>(ctx->dScratch);
+  T* partial = out + kb;
+  k_trans_mv<T, KT, BT><<<dim3(tiles, slices), kBlock, 0, ctx->stream>>>(tableOf<T>(A), k, tableOf<T>(X), b, A->ld, tilesB, partial);
+  LAUNCH_CHECK(ctx);
+  k_reduce_partials<T><<<int(kb), kBlock, 0, ctx->stream>>>(partial, slices, out);
+  LAUNCH_CHECK(ctx);
+  rc = allReduceScratch(ctx, kb * w);
+  if (rc) return rc;
+  std::vector<double> tmp(kb * w);
+  rc = fetchScratch(ctx, tmp.data(), kb * w);
+  if (rc) return rc;
+  const T a = scalarOf<T>(alpha);
+  T* Bt = reinterpret_cast<T*>(B);
+  const T* src = reinterpret_cast<const T*>(tmp.data());
+  for (int j = 0; j < b; ++j)
+    for (int i = 0; i < k; ++i) Bt[i + size_t(j) * ldb] = a * src[i + size_t(j) * k];
+  return MXG_OK;
+}
+
+template <class T>
+int timesMatImpl(const double alpha[2], const mxg_mv* A, const double* B, int ldb, const double beta[2], mxg_mv* Y) {
+  mxg_ctx* ctx = A->map->ctx;
+  if (Y->ld == 0) return MXG_OK;
+  constexpr int w = sizeof(T) / sizeof(double);
+  constexpr int BT = (w == 1) ? 8 : 4;
+  const int k = A->ncols, b = Y->ncols;
+  const T al = scalarOf<T>(alpha), be = scalarOf<T>(beta);
+  const bool useY = !isZero(be);
+  // columns of B that fit in one parameter block
+  const int colsPerLaunch = kMaxBParam / (k * w);
+  MXG_REQUIRE(colsPerLaunch >= 1, "mxg_mv_times_mat_add_mv: A has too many columns (%d) for one pass", k);
+  const int grid = gridFor(ctx, Y->ld, kBlock, 8);
+  for (int c0 = 0; c0 < b; c0 += colsPerLaunch) {
+    const int cc = (b - c0 < colsPerLaunch) ? b - c0 : colsPerLaunch;
+    DenseParam P;
+    for (int j = 0; j < cc; ++j)
+      std::memcpy(&P.v[size_t(j) * k * w], B + (size_t(c0 + j) * ldb) * w, sizeof(double) * k * w);
+    // view of Y's columns c0..c0+cc
+    ColTable<T> ty = tableOf<T>(Y, c0, cc);
+    for (int j0 = 0; j0 < cc; j0 += BT) {
+      const int bc = (cc - j0 < BT) ? cc - j0 : BT;
+      k_times_mat<T, BT><<<grid, kBlock, 0, ctx->stream>>>(tableOf<T>(A), k, P, j0, bc, al, be, useY, ty, Y->ld);
+      LAUNCH_CHECK(ctx);
+    }
+  }
+  return MXG_OK;
+}
+
+bool overlaps(const mxg_mv* a, const mxg_mv* b) {
+  if (a->storage.get() != b->storage.get()) return false;
+  for (void* pa : a->col)
+    for (void* pb : b->col)
+      if (pa == pb) return true;
+  return false;
+}
+
+int checkSame(const char* fn, const mxg_mv* a, const mxg_mv* b, bool sameCols = true) {
+  MXG_REQUIRE(a && b, "%s: NULL multivector", fn);
+  MXG_REQUIRE(a->map->ctx == b->map->ctx, "%s: operands live on different contexts", fn);
+  MXG_REQUIRE(a->ld == b->ld && a->map->nGlobal == b->map->nGlobal, "%s: operands have different maps", fn);
+  MXG_REQUIRE(a->isComplex == b->isComplex, "%s: mixed real/complex operands", fn);
+  if (sameCols) MXG_REQUIRE(a->ncols == b->ncols, "%s: column counts differ (%d vs %d)", fn, a->ncols, b->ncols);
+  return MXG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mxg_mv_fill(mxg_mv* mv, const double alpha[2]) {
+  MXG_REQUIRE(mv && alpha, "mxg_mv_fill: NULL argument");
+  MXG_CUDA(cudaSetDevice(mv->map->ctx->device));
+  return mv->isComplex ? fillImpl<zd>(mv, alpha) : fillImpl<double>(mv, alpha);
+}
+
+int mxg_mv_scale(mxg_mv* mv, const double alpha[2]) {
+  MXG_REQUIRE(mv && alpha, "mxg_mv_scale: NULL argument");
+  MXG_CUDA(cudaSetDevice(mv->map->ctx->device));
+  return mv->isComplex ? scaleColsImpl<zd>(mv, alpha, true) : scaleColsImpl<double>(mv, alpha, true);
+}
+
+int mxg_mv_scale_cols(mxg_mv* mv, const double* alphas) {
+  MXG_REQUIRE(mv && alphas, "mxg_mv_scale_cols: NULL argument");
+  MXG_CUDA(cudaSetDevice(mv->map->ctx->device));
+  return mv->isComplex ? scaleColsImpl<zd>(mv, alphas, false) : scaleColsImpl<double>(mv, alphas, false);
+}
+
+int mxg_mv_conj(mxg_mv* mv) {
+  MXG_REQUIRE(mv, "mxg_mv_conj: NULL argument");
+  if (!mv->isComplex || mv->ld == 0) return MXG_OK;  // MxMultiVector.cpp:128-129: no-op for real
+  mxg_ctx* ctx = mv->map->ctx;
+  MXG_CUDA(cudaSetDevice(ctx->device));
+  k_conj<<<gridCols<zd>(ctx, mv->ld, mv->ncols), kBlock, 0, ctx->stream>>>(tableOf<zd>(mv), mv->ld);
+  LAUNCH_CHECK(ctx);
+  return MXG_OK;
+}
+
+int mxg_mv_random(mxg_mv* mv, uint64_t seed) {
+  MXG_REQUIRE(mv, "mxg_mv_random: NULL argument");
+  if (mv->ld == 0) return MXG_OK;
+  mxg_ctx* ctx = mv->map->ctx;
+  MXG_CUDA(cudaSetDevice(ctx->device));
+  ColIds ids;
+  for (int j = 0; j < mv->ncols; ++j) ids.v[j] = mv->baseCol[j];
+  if (mv->isComplex)
+    k_random_cplx<<<gridCols<zd>(ctx, mv->ld, mv->ncols), kBlock, 0, ctx->stream>>>(tableOf<zd>(mv), ids, mv->map->dGids, mv->ld, seed);
+  else
+    k_random_real<<<gridCols<double>(ctx, mv->ld, mv->ncols), kBlock, 0, ctx->stream>>>(tableOf<double>(mv), ids, mv->map->dGids, mv->ld, seed);
+  LAUNCH_CHECK(ctx);
+  return MXG_OK;
+}
+
+int mxg_mv_add_mv(mxg_mv* dst, const double alpha[2], const mxg_mv* A, const double beta[2], const mxg_mv* B) {
+  int rc = checkSame("mxg_mv_add_mv", dst, A);
+  if (rc) return rc;
+  rc = checkSame("mxg_mv_add_mv", dst, B);
+  if (rc) return rc;
+  MXG_REQUIRE(alpha && beta, "mxg_mv_add_mv: NULL scalar");
+  MXG_CUDA(cudaSetDevice(dst->map->ctx->device));
+  return dst->isComplex ? axpbyImpl<zd>(dst, alpha, A, beta, B) : axpbyImpl<double>(dst, alpha, A, beta, B);
+}
+
+int mxg_mv_update(mxg_mv* dst, const double a[2], const mxg_mv* A, const double s[2]) {
+  return mxg_mv_add_mv(dst, a, A, s, dst);
+}
+
+int mxg_mv_assign(mxg_mv* dst, const mxg_mv* src) {
+  int rc = checkSame("mxg_mv_assign", dst, src);
+  if (rc) return rc;
+  if (dst->ld == 0) return MXG_OK;
+  mxg_ctx* ctx = dst->map->ctx;
+  MXG_CUDA(cudaSetDevice(ctx->device));
+  if (dst->isComplex)
+    k_copy<zd><<<gridCols<zd>(ctx, dst->ld, dst->ncols), kBlock, 0, ctx->stream>>>(tableOf<zd>(dst), tableOf<zd>(src), dst->ld);
+  else
+    k_copy<double><<<gridCols<double>(ctx, dst->ld, dst->ncols), kBlock, 0, ctx->stream>>>(tableOf<double>(dst), tableOf<double>(src), dst->ld);
+  LAUNCH_CHECK(ctx);
+  return MXG_OK;
+}
+
+int mxg_mv_set_block(mxg_mv* dst, const mxg_mv* src, const int* index, int n) {
+  int rc = checkSame("mxg_mv_set_block", dst, src, false);
+  if (rc) return rc;
+  MXG_REQUIRE(index && n >= 1 && n <= src->ncols, "mxg_mv_set_block: bad index list");
+  for (int j = 0; j < n; ++j)
+    MXG_REQUIRE(index[j] >= 0 && index[j] < dst->ncols, "mxg_mv_set_block: index %d out of range", index[j]);
+  std::vector<int> cols(index, index + n);
+  mxg_mv* view = nullptr;
+  rc = mxg_mv_view(dst, cols.data(), n, &view);
+  if (rc) return rc;
+  mxg_mv* sview = nullptr;
+  std::vector<int> first(n);
+  for (int j = 0; j < n; ++j) first[j] = j;
+  rc = mxg_mv_view(const_cast<mxg_mv*>(src), first.data(), n, &sview);
+  if (rc == MXG_OK) rc = mxg_mv_assign(view, sview);
+  if (sview) mxg_mv_destroy(sview);
+  mxg_mv_destroy(view);
+  return rc;
+}
+
+int mxg_mv_dot(const mxg_mv* a, const mxg_mv* b, double* out) {
+  int rc = checkSame("mxg_mv_dot", a, b);
+  if (rc) return rc;
+  MXG_REQUIRE(out, "mxg_mv_dot: out is NULL");
+  mxg_ctx* ctx = a->map->ctx;
+  MXG_CUDA(cudaSetDevice(ctx->device));
+  rc = a->isComplex ? dotToScratch<zd>(a, b) : dotToScratch<double>(a, b);
+  if (rc) return rc;
+  return fetchScratch(ctx, out, size_t(a->ncols) * (a->isComplex ? 2 : 1));
+}
+
+int mxg_mv_norm2(const mxg_mv* mv, double* out) {
+  MXG_REQUIRE(mv && out, "mxg_mv_norm2: NULL argument");
+  mxg_ctx* ctx = mv->map->ctx;
+  MXG_CUDA(cudaSetDevice(ctx->device));
+  int rc = mv->isComplex ? dotToScratch<zd>(mv, mv) : dotToScratch<double>(mv, mv);
+  if (rc) return rc;
+  const int w = mv->isComplex ? 2 : 1;
+  std::vector<double> tmp(size_t(mv->ncols) * w);
+  rc = fetchScratch(ctx, tmp.data(), tmp.size());
+  if (rc) return rc;
+  for (int j = 0; j < mv->ncols; ++j) out[j] = std::sqrt(tmp[size_t(j) * w]);
+  return MXG_OK;
+}
+
+int mxg_mv_normalize(mxg_mv* mv) {
+  MXG_REQUIRE(mv, "mxg_mv_normalize: NULL argument");
+  std::vector<double> nrm(mv->ncols);
+  int rc = mxg_mv_norm2(mv, nrm.data());
+  if (rc) return rc;
+  const int w = mv->isComplex ? 2 : 1;
+  std::vector<double> inv(size_t(mv->ncols) * w, 0.0);
+  for (int j = 0; j < mv->ncols; ++j) inv[size_t(j) * w] = nrm[j] > 0 ? 1.0 / nrm[j] : 0.0;
+  return mxg_mv_scale_cols(mv, inv.data());
+}
+
+int mxg_mv_trans_mv(const double alpha[2], const mxg_mv* A, const mxg_mv* X, double* B, int ldb) {
+  int rc = checkSame("mxg_mv_trans_mv", A, X, false);
+  if (rc) return rc;
+  MXG_REQUIRE(alpha && B && ldb >= A->ncols, "mxg_mv_trans_mv: bad B / ldb (need ldb >= %d)", A->ncols);
+  MXG_CUDA(cudaSetDevice(A->map->ctx->device));
+  return A->isComplex ? transMvImpl<zd>(alpha, A, X, B, ldb) : transMvImpl<double>(alpha, A, X, B, ldb);
+}
+
+int mxg_mv_times_mat_add_mv(const double alpha[2], const mxg_mv* A, const double* B, int ldb, const double beta[2], mxg_mv* Y) {
+  int rc = checkSame("mxg_mv_times_mat_add_mv", A, Y, false);
+  if (rc) return rc;
+  MXG_REQUIRE(alpha && beta && B && ldb >= A->ncols, "mxg_mv_times_mat_add_mv: bad B / ldb (need ldb >= %d)", A->ncols);
+  MXG_REQUIRE(!overlaps(A, Y), "mxg_mv_times_mat_add_mv: A and Y must not share columns");
+  MXG_CUDA(cudaSetDevice(A->map->ctx->device));
+  return A->isComplex ? timesMatImpl<zd>(alpha, A, B, ldb, beta, Y) : timesMatImpl<double>(alpha, A, B, ldb, beta, Y);
+}
+
+}  // extern "C"
