@@ -127,7 +127,11 @@ __device__ __forceinline__ void storeY(T* y, int64_t row, T acc, const Epilogue<
   else y[row] = ep.alpha * acc + ep.beta * y[row];
 }
 
-// Dictionary rows: one thread per row.
+// Dictionary rows: one thread per row. The entry loop is unrolled by kUnroll with all table and
+// x loads of a group issued before the (ordered) accumulation, so each thread keeps 2*kUnroll
+// independent loads in flight.
+constexpr int kUnroll = 4;
+
 template <class T, bool GHOST, int NV>
 __global__ void __launch_bounds__(kBlock) k_spmm_dict(int64_t rowBegin, int64_t rowEnd, const int32_t* __restrict__ rowPat,
                                                       const int32_t* __restrict__ patOff, const PatEntry<T>* __restrict__ pat,
@@ -141,13 +145,23 @@ __global__ void __launch_bounds__(kBlock) k_spmm_dict(int64_t rowBegin, int64_t 
     T acc[NV];
 #pragma unroll
     for (int jj = 0; jj < NV; ++jj) acc[jj] = zeroOf<T>();
-    for (int32_t q = o; q < oe; ++q) {
-      const PatEntry<T> e = pat[q];
-      const int64_t c = row + e.d;
-      const T v = entryVal(e);
+    for (int32_t q = o; q < oe; q += kUnroll) {
+      PatEntry<T> e[kUnroll];
+      T xv[kUnroll][NV];
 #pragma unroll
-      for (int jj = 0; jj < NV; ++jj)
-        if (NV == 1 || j0 + jj < nvec) accum(acc[jj], v, loadX<T, GHOST>(X, j0 + jj, c));
+      for (int u = 0; u < kUnroll; ++u) e[u] = pat[min(q + u, oe - 1)];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+        for (int jj = 0; jj < NV; ++jj)
+          xv[u][jj] = loadX<T, GHOST>(X, min(j0 + jj, nvec - 1), row + e[u].d);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (q + u < oe) {
+          const T v = entryVal(e[u]);
+#pragma unroll
+          for (int jj = 0; jj < NV; ++jj) accum(acc[jj], v, xv[u][jj]);
+        }
     }
 #pragma unroll
     for (int jj = 0; jj < NV; ++jj)
@@ -155,7 +169,9 @@ __global__ void __launch_bounds__(kBlock) k_spmm_dict(int64_t rowBegin, int64_t 
   }
 }
 
-// General rows: sliced ELL, slice height 32, one thread per (compacted) row.
+// General rows: sliced ELL, slice height 32, one thread per (compacted) row. The loop runs
+// over the slice width (uniform across the warp); entries past a row's own length are
+// zero-padding and are skipped in the accumulation, which keeps the result bit-exact.
 template <class T, bool GHOST, int NV>
 __global__ void __launch_bounds__(kBlock) k_spmm_sell(int64_t genBegin, int64_t genEnd, const int32_t* __restrict__ genRow,
                                                       const int32_t* __restrict__ genLen, const int64_t* __restrict__ slicePtr,
@@ -165,23 +181,41 @@ __global__ void __launch_bounds__(kBlock) k_spmm_sell(int64_t genBegin, int64_t 
   const int64_t i = genBegin + blockIdx.x * int64_t(kBlock) + threadIdx.x;
   if (i >= genEnd) return;
   const int64_t row = genRow[i];
-  if (row < 0) return;  // slice padding
-  const int len = genLen[i];
-  const int64_t base = slicePtr[i >> 5] + (i & 31);
+  const int len = row < 0 ? 0 : genLen[i];
+  const int64_t sp = slicePtr[i >> 5];
+  const int width = int((slicePtr[(i >> 5) + 1] - sp) >> 5);
+  const int64_t base = sp + (i & 31);
   for (int j0 = 0; j0 < nvec; j0 += NV) {
     T acc[NV];
 #pragma unroll
     for (int jj = 0; jj < NV; ++jj) acc[jj] = zeroOf<T>();
-    for (int k = 0; k < len; ++k) {
-      const int64_t c = col[base + int64_t(k) * 32];
-      const T v = val[base + int64_t(k) * 32];
+    for (int k = 0; k < width; k += kUnroll) {
+      int32_t c[kUnroll];
+      T v[kUnroll];
+      T xv[kUnroll][NV];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t at = base + int64_t(min(k + u, width - 1)) * 32;
+        c[u] = col[at];
+        v[u] = val[at];
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+        for (int jj = 0; jj < NV; ++jj)
+          xv[u][jj] = loadX<T, GHOST>(X, min(j0 + jj, nvec - 1), c[u]);  // padding holds a valid index
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (k + u < len) {
+#pragma unroll
+          for (int jj = 0; jj < NV; ++jj) accum(acc[jj], v[u], xv[u][jj]);
+        }
+    }
+    if (row >= 0) {
 #pragma unroll
       for (int jj = 0; jj < NV; ++jj)
-        if (NV == 1 || j0 + jj < nvec) accum(acc[jj], v, loadX<T, GHOST>(X, j0 + jj, c));
+        if (NV == 1 || j0 + jj < nvec) storeY(Y.p[j0 + jj], row, acc[jj], ep);
     }
-#pragma unroll
-    for (int jj = 0; jj < NV; ++jj)
-      if (NV == 1 || j0 + jj < nvec) storeY(Y.p[j0 + jj], row, acc[jj], ep);
   }
 }
 
@@ -557,6 +591,17 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
   A->ellEntries = slicePtr[nSlices];
   std::vector<int32_t> ellCol(A->ellEntries, 0);
   std::vector<T> ellVal(A->ellEntries, zeroOf<T>());
+  for (int64_t sIdx = 0; sIdx < nSlices; ++sIdx) {
+    // padding entries point at a column some real entry of the slice uses, so the kernel may
+    // load through them unconditionally (their value is 0 and they are skipped in the sum)
+    int32_t fallback = 0;
+    bool have = false;
+    for (int l = 0; l < 32 && !have; ++l) {
+      const int64_t i = sIdx * 32 + l;
+      if (genRow[i] >= 0 && genLen[i] > 0) { fallback = ext[rp[genRow[i]]]; have = true; }
+    }
+    for (int64_t q = slicePtr[sIdx]; q < slicePtr[sIdx + 1]; ++q) ellCol[q] = fallback;
+  }
   for (int64_t i = 0; i < A->nGen; ++i) {
     const int64_t r = genRow[i];
     if (r < 0) continue;

@@ -1,0 +1,63 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/mxgpu.h declares."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mxgpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mxg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(mx):
+    syms = declared_symbols()
+    assert len(syms) >= 45
+    out = subprocess.check_output(["nm", "-D", "--defined-only", mx.library_path()], text=True)
+    exported = set(re.findall(r" T (mxg_[a-z0-9_]+)", out))
+    missing = [s for s in syms if s not in exported]
+    assert not missing, "declared in mxgpu.h but not exported: %s" % missing
+    L = mx.load_library()
+    for s in syms:
+        assert hasattr(L, s)
+    assert L.mxg_version() >= 100
+
+
+def test_no_cpu_fallback(mx):
+    """Without a CUDA device the product path must fail loudly, never fall back."""
+    import ctypes as C
+    L = mx.load_library()
+    h = C.c_void_p()
+    rc = L.mxg_ctx_create(0, C.byref(h))
+    if rc == 0:
+        L.mxg_ctx_destroy(h)
+        pytest.skip("a GPU is present")
+    assert rc < 0
+    assert b"no CPU fallback" in L.mxg_last_error()
+    with pytest.raises(mx.MxError):
+        mx.Context(0)
+
+
+def test_product_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under maxwell_b200/ or include/ may reference it."""
+    bad = []
+    for base in ("maxwell_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".h", ".hpp", ".cpp")):
+                    txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                    if re.search(r"(from|import)\s+oracle|liboracle|mxo_", txt):
+                        bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+
+
+def test_hash_uniform_range(mx):
+    import numpy as np
+    v = mx.hash_uniform(12345, np.arange(100000), 0)
+    assert v.min() >= -1.0 and v.max() < 1.0
+    assert abs(v.mean()) < 0.01 and abs(v.std() - 1 / np.sqrt(3)) < 0.01
+    assert not np.array_equal(v, mx.hash_uniform(12345, np.arange(100000), 1))
