@@ -129,6 +129,10 @@ int mxg_mv_times_mat_add_mv(const double alpha[2], const mxg_mv* A, const double
  * host layout: column-major, leading dimension ld (in scalars) */
 int mxg_mv_upload(mxg_mv* mv, const double* host, int64_t ld);
 int mxg_mv_download(const mxg_mv* mv, double* host, int64_t ld);
+/* the map a multivector / operator lives on (borrowed handle; getMap(), getRangeMap(), getDomainMap()) */
+mxg_map* mxg_mv_get_map(const mxg_mv* mv);
+mxg_map* mxg_crs_row_map(const mxg_crs* A);
+mxg_map* mxg_crs_domain_map(const mxg_crs* A);
 /* device pointer of column j (for host code that enqueues its own kernels) */
 void* mxg_mv_col_ptr(mxg_mv* mv, int j);
 
@@ -160,6 +164,34 @@ int mxg_crs_apply_timed(const mxg_crs* A, const mxg_mv* x, mxg_mv* y, double ms[
  * [3]=distinct row patterns, [4]=device bytes of the matrix layout, [5]=ghost entries,
  * [6]=rows that need ghosts, [7]=padded ELL entries */
 int mxg_crs_stats(const mxg_crs* A, int64_t out[8]);
+/* y = d .* x with d a one-column multivector: diagonal operators such as mRhs = dmA
+ * (MxMagWaveOp.cpp:227-241, applied at :865,895,1132) without a CRS round trip */
+int mxg_mv_diag_mult(mxg_mv* y, const mxg_mv* d, const mxg_mv* x);
+
+/* ---- geometric multigrid preconditioner (MxGeoMultigridPrec.{h,cpp}; dead code in the
+ * reference, so this follows its structure: setup :98-240, vCycle :243-398, fullVCycle
+ * :547-616, ApplyInverse :496-542). Levels are ordered fine -> coarse. ops[l] must be square
+ * on one map; restrictors[l] maps level l -> l+1, prolongators[l] maps level l+1 -> l.
+ * The handles are borrowed: they must outlive the preconditioner. ------------------------ */
+typedef struct mxg_gmg mxg_gmg;
+typedef struct mxg_gmg_params {
+  int smoother_degree;      /* Chebyshev degree per smoothing step ("smoother sweeps")      */
+  double eig_ratio;         /* smoother targets [lmax/ratio, 1.1*lmax] ("ratio eigenvalue") */
+  int cycles;               /* V-cycles per apply ("cycles")                                 */
+  int coarse_degree;        /* Chebyshev degree of the coarsest-level solve (replaces KLU)  */
+  double coarse_eig_ratio;
+  int full_multigrid;       /* 1: fullVCycle (FMG), 0: plain V-cycles from a zero guess     */
+  int power_iterations;     /* iterations of the lambda_max(D^-1 A) estimate at setup       */
+} mxg_gmg_params;
+void mxg_gmg_default_params(mxg_gmg_params* p);
+int mxg_gmg_create(mxg_ctx* ctx, int nlevels, mxg_crs* const* ops, mxg_crs* const* restrictors,
+                   mxg_crs* const* prolongators, const mxg_gmg_params* params, mxg_gmg** out);
+int mxg_gmg_destroy(mxg_gmg* g);
+/* ApplyInverse: x = M^-1 b for a block of right-hand sides */
+int mxg_gmg_apply(mxg_gmg* g, const mxg_mv* b, mxg_mv* x);
+/* out[0]=rows, [1]=nnz, [2]=lambda_max estimate of D^-1 A on that level, [3]=SpMM count so far */
+int mxg_gmg_info(const mxg_gmg* g, int level, double out[4]);
+
 /* number of kernels this library has launched on ctx since creation (bench bookkeeping) */
 int64_t mxg_ctx_launch_count(const mxg_ctx* ctx);
 

@@ -1,0 +1,37 @@
+/* libmxsolver -- C entry points of the host-side eigensolver driver (C++: include/mx/MxSolver.hpp).
+ * Replaces MxSolver::solve + the Anasazi solver manager it drives (reference src/MxSolver.cpp:100-239):
+ * lowest eigenpairs of A x = theta M x on the GPU through libmxgpu. Plain handles only. */
+#ifndef MXSOLVER_H
+#define MXSOLVER_H
+#include "mxgpu.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mxs_params {
+  int nev;          /* wanted eigenpairs ("eigensolver : nev", MxSolver.cpp:37) */
+  int block_size;   /* 0 = nev + max(4, nev/2) */
+  int max_iters;
+  double tol;       /* |A x - theta M x| / (|theta| |M x|) */
+  int verbose;
+  uint64_t seed;
+  int random_init;  /* 1: start from MvRandom (MxSolver.cpp:62-64), 0: use X as given */
+} mxs_params;
+
+void mxs_default_params(mxs_params* p);
+const char* mxs_last_error(void);
+/* A: assembled operator (curlCurl or vecLapl); m_diag: one-column multivector holding the diagonal
+ * of the mass matrix mRhs (NULL = identity); prec: multigrid preconditioner (NULL = none).
+ * X: n x block multivector, receives the M-orthonormal Ritz vectors.
+ * evals/resnorms: block entries. info[0]=iterations, [1]=converged among nev, [2]=A applies (columns),
+ * [3]=preconditioner applies (columns). */
+int mxs_lobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, mxg_mv* X, const mxs_params* p,
+               double* evals, double* resnorms, int64_t info[4], double* seconds);
+/* acceptance metrics of MxMagWaveOp::checkEigensolution / checkDivergences (MxMagWaveOp.cpp:1118-1234):
+ * res[j] = |A x_j - theta_j M x_j|_2 / |theta_j| ; div[j] = |D M x_j|_2 / |M x_j|_2 (D may be NULL) */
+int mxs_check_eigensolution(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_crs* divB, mxg_mv* X, const double* evals,
+                            double* res, double* div);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -90,6 +90,15 @@ def load_library():
         "mxg_crs_apply": (i32, [vp, vp, vp]),
         "mxg_crs_apply_axpby": (i32, [vp, dp, vp, dp, vp]),
         "mxg_crs_stats": (i32, [vp, vp]),
+        "mxg_mv_get_map": (vp, [vp]),
+        "mxg_crs_row_map": (vp, [vp]),
+        "mxg_crs_domain_map": (vp, [vp]),
+        "mxg_mv_diag_mult": (i32, [vp, vp, vp]),
+        "mxg_gmg_default_params": (None, [vp]),
+        "mxg_gmg_create": (i32, [vp, i32, vp, vp, vp, vp, pvp]),
+        "mxg_gmg_destroy": (i32, [vp]),
+        "mxg_gmg_apply": (i32, [vp, vp, vp]),
+        "mxg_gmg_info": (i32, [vp, i32, dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -99,7 +108,41 @@ def load_library():
     return L
 
 
-EXPORTED_SYMBOLS = None  # filled lazily by exported_symbols()
+_SOLVER = None
+
+
+class GmgParams(C.Structure):
+    """mxg_gmg_params (include/mxgpu.h)."""
+    _fields_ = [("smoother_degree", C.c_int), ("eig_ratio", C.c_double), ("cycles", C.c_int), ("coarse_degree", C.c_int),
+                ("coarse_eig_ratio", C.c_double), ("full_multigrid", C.c_int), ("power_iterations", C.c_int)]
+
+
+class SolverParams(C.Structure):
+    """mxs_params (include/mxsolver.h)."""
+    _fields_ = [("nev", C.c_int), ("block_size", C.c_int), ("max_iters", C.c_int), ("tol", C.c_double), ("verbose", C.c_int),
+                ("seed", C.c_uint64), ("random_init", C.c_int)]
+
+
+def load_solver():
+    """dlopen libmxsolver.so (host C++ driver above the C ABI: include/mx/MxSolver.hpp)."""
+    global _SOLVER
+    if _SOLVER is not None:
+        return _SOLVER
+    load_library()
+    path = os.path.join(_HERE, "libmxsolver.so")
+    if not os.path.exists(path):
+        raise MxError("libmxsolver.so not built (run `python __graft_entry__.py`)")
+    S = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    vp, dp = C.c_void_p, C.POINTER(C.c_double)
+    S.mxs_default_params.restype = None
+    S.mxs_default_params.argtypes = [vp]
+    S.mxs_last_error.restype = C.c_char_p
+    S.mxs_lobpcg.restype = C.c_int
+    S.mxs_lobpcg.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, dp]
+    S.mxs_check_eigensolution.restype = C.c_int
+    S.mxs_check_eigensolution.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    _SOLVER = S
+    return S
 
 
 def _ck(rc):
@@ -445,3 +488,94 @@ def hash_uniform(seed, gids, col, part=0):
         z *= np.uint64(0x94D049BB133111EB)
         z ^= z >> np.uint64(31)
         return 2.0 * ((z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)) - 1.0
+
+
+def diag_mult(y, d, x):
+    """y = d .* x with d a one-column multivector (mRhs = dmA; MxMagWaveOp.cpp:865,895)."""
+    _ck(load_library().mxg_mv_diag_mult(y.h, d.h, x.h))
+
+
+class MxGeoMultigridPrec:
+    """GPU V-cycle / FMG preconditioner (spec: reference src/MxGeoMultigridPrec.cpp; dead code there).
+
+    ops[l]: level operators fine -> coarse; restrictors[l]: level l -> l+1; prolongators[l]: l+1 -> l.
+    Keyword parameters mirror the reference's "linear solver : ..." keys (MxGeoMultigridPrec.cpp:100-108).
+    """
+
+    def __init__(self, ctx, ops, restrictors, prolongators, smoother_sweeps=2, cycles=1, eig_ratio=30.0,
+                 coarse_degree=30, coarse_eig_ratio=1000.0, full_multigrid=False, power_iterations=30):
+        self._L = load_library()
+        self._keep = (list(ops), list(restrictors), list(prolongators))
+        p = GmgParams()
+        self._L.mxg_gmg_default_params(C.byref(p))
+        p.smoother_degree, p.cycles, p.eig_ratio = int(smoother_sweeps), int(cycles), float(eig_ratio)
+        p.coarse_degree, p.coarse_eig_ratio = int(coarse_degree), float(coarse_eig_ratio)
+        p.full_multigrid, p.power_iterations = int(bool(full_multigrid)), int(power_iterations)
+        n = len(ops)
+        arr = lambda xs: (C.c_void_p * max(len(xs), 1))(*[x.h for x in xs])
+        h = C.c_void_p()
+        _ck(self._L.mxg_gmg_create(ctx.h, n, arr(ops), arr(restrictors), arr(prolongators), C.byref(p), C.byref(h)))
+        self.h = h
+        self.nlevels = n
+
+    def ApplyInverse(self, b, x):
+        _ck(self._L.mxg_gmg_apply(self.h, b.h, x.h))
+
+    def info(self, level):
+        out = (C.c_double * 4)()
+        _ck(self._L.mxg_gmg_info(self.h, level, out))
+        return {"rows": int(out[0]), "nnz": int(out[1]), "lambda_max": out[2], "spmm_count": int(out[3])}
+
+    def __del__(self):
+        try:
+            if self.h:
+                self._L.mxg_gmg_destroy(self.h)
+        except Exception:
+            pass
+
+
+class MxSolver:
+    """Block eigensolver driver (reference: src/MxSolver.cpp:22-239 driving Anasazi): lowest eigenpairs of
+    A x = theta M x with an optional multigrid preconditioner. The loop runs in C++ (include/mx/MxSolver.hpp)."""
+
+    def __init__(self, ctx, A, m_diag=None, prec=None, nev=10, block_size=0, tol=1e-8, max_iters=300, verbose=0, seed=12345):
+        self._S = load_solver()
+        self.ctx, self.A, self.m_diag, self.prec = ctx, A, m_diag, prec
+        p = SolverParams()
+        self._S.mxs_default_params(C.byref(p))
+        p.nev, p.block_size, p.tol, p.max_iters, p.verbose, p.seed = int(nev), int(block_size), float(tol), int(max_iters), int(verbose), int(seed)
+        if p.block_size <= 0:
+            p.block_size = nev + max(4, nev // 2)
+        self.params = p
+
+    def solve(self, X=None):
+        m = self.params.block_size
+        if X is None:
+            X = MxMultiVector(self.A.row_map, m)
+            self.params.random_init = 1
+        else:
+            self.params.random_init = 0
+        ev = np.zeros(m)
+        rs = np.zeros(m)
+        info = (C.c_int64 * 4)()
+        sec = C.c_double()
+        rc = self._S.mxs_lobpcg(self.ctx.h, self.A.h, self.m_diag.h if self.m_diag is not None else None,
+                                self.prec.h if self.prec is not None else None, X.h, C.byref(self.params),
+                                ev.ctypes.data, rs.ctypes.data, info, C.byref(sec))
+        if rc != 0:
+            raise MxError(self._S.mxs_last_error().decode())
+        self.eigenvalues, self.residuals, self.eigenvectors = ev, rs, X
+        self.iterations, self.converged, self.apply_a, self.apply_prec = info[0], info[1], info[2], info[3]
+        self.seconds = sec.value
+        return ev[: self.params.nev]
+
+    def check(self, div_op=None):
+        """checkEigensolution / checkDivergences (MxMagWaveOp.cpp:1118-1234)."""
+        m = self.params.block_size
+        res, div = np.zeros(m), np.zeros(m)
+        rc = self._S.mxs_check_eigensolution(self.ctx.h, self.A.h, self.m_diag.h if self.m_diag is not None else None,
+                                             div_op.h if div_op is not None else None, self.eigenvectors.h,
+                                             self.eigenvalues.ctypes.data, res.ctypes.data, div.ctypes.data)
+        if rc != 0:
+            raise MxError(self._S.mxs_last_error().decode())
+        return res, div

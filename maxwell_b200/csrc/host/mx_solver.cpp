@@ -1,0 +1,106 @@
+// libmxsolver: C entry points around include/mx/MxSolver.hpp (host C++, no CUDA in this file).
+#include "mxsolver.h"
+
+#include <cstring>
+#include <string>
+
+#include "mx/MxSolver.hpp"
+
+namespace {
+thread_local std::string g_err;
+struct Wrapped {
+  std::shared_ptr<MxComm> comm;
+  std::shared_ptr<MxMap> map;
+};
+Wrapped wrap(mxg_ctx* ctx, mxg_mv* X) {
+  Wrapped w;
+  w.comm = std::make_shared<MxComm>(ctx, false);
+  w.map = std::make_shared<MxMap>(mxg_mv_get_map(X), w.comm, false);
+  return w;
+}
+}  // namespace
+
+extern "C" {
+
+void mxs_default_params(mxs_params* p) {
+  if (!p) return;
+  MxSolverParams d;
+  p->nev = d.nev;
+  p->block_size = 0;
+  p->max_iters = d.maxIters;
+  p->tol = d.tol;
+  p->verbose = 0;
+  p->seed = d.seed;
+  p->random_init = 1;
+}
+
+const char* mxs_last_error(void) { return g_err.c_str(); }
+
+int mxs_lobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, mxg_mv* X, const mxs_params* p,
+               double* evals, double* resnorms, int64_t info[4], double* seconds) {
+  try {
+    if (!ctx || !A || !X || !p) throw std::runtime_error("mxs_lobpcg: NULL argument");
+    if (mxg_mv_is_complex(X)) throw std::runtime_error("mxs_lobpcg: complex problems are not supported by this driver yet");
+    Wrapped w = wrap(ctx, X);
+    MxAnasaziMV<double> Xmv(X, w.map, false);
+    MxCrsOperator<double> Aop(A);
+    std::unique_ptr<MxDiagOperator<double>> Mop;
+    if (m_diag) Mop.reset(new MxDiagOperator<double>(m_diag));
+    std::unique_ptr<MxGeoMultigridPrec<double>> Top;
+    if (prec) Top.reset(new MxGeoMultigridPrec<double>(prec, false));
+    MxSolverParams sp;
+    sp.nev = p->nev;
+    sp.blockSize = p->block_size > 0 ? p->block_size : mxg_mv_num_cols(X);
+    sp.maxIters = p->max_iters;
+    sp.tol = p->tol;
+    sp.verbose = p->verbose;
+    sp.seed = p->seed;
+    sp.randomInit = p->random_init != 0;
+    MxSolver solver(&Aop, Mop.get(), Top.get(), sp);
+    MxSolverResult r = solver.solve(Xmv);
+    const int m = sp.blockSize;
+    if (evals) std::memcpy(evals, r.eigenvalues.data(), sizeof(double) * m);
+    if (resnorms) std::memcpy(resnorms, r.residuals.data(), sizeof(double) * m);
+    if (info) { info[0] = r.iterations; info[1] = r.converged; info[2] = r.applyA; info[3] = r.applyPrec; }
+    if (seconds) *seconds = r.seconds;
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+int mxs_check_eigensolution(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_crs* divB, mxg_mv* X, const double* evals,
+                            double* res, double* div) {
+  try {
+    if (!ctx || !A || !X || !evals) throw std::runtime_error("mxs_check_eigensolution: NULL argument");
+    Wrapped w = wrap(ctx, X);
+    MxAnasaziMV<double> Xmv(X, w.map, false);
+    const int m = Xmv.GetNumberVecs();
+    MxAnasaziMV<double> AX(w.map, m), MX(w.map, m);
+    MxCrsOperator<double>(A).Apply(Xmv, AX);
+    if (m_diag) MxDiagOperator<double>(m_diag).Apply(Xmv, MX); else MX = Xmv;
+    std::vector<double> th(evals, evals + m), rn, mn;
+    MxAnasaziMV<double> scaled(MX);
+    scaled.MvScale(th);
+    AX.MvAddMv(1.0, AX, -1.0, scaled);
+    AX.MvNorm(rn);
+    MX.MvNorm(mn);
+    for (int j = 0; j < m; ++j) res[j] = rn[j] / std::fabs(evals[j]);   // MxMagWaveOp.cpp:1195-1203
+    if (divB && div) {
+      mxg_mv* d = nullptr;
+      mx::check(mxg_mv_create(mxg_crs_row_map(divB), m, 0, &d));
+      mx::check(mxg_crs_apply(divB, MX.getRawMV(), d));
+      std::vector<double> dn(m);
+      mx::check(mxg_mv_norm2(d, dn.data()));
+      mxg_mv_destroy(d);
+      for (int j = 0; j < m; ++j) div[j] = mn[j] > 0 ? dn[j] / mn[j] : 0.0;
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+}  // extern "C"

@@ -296,6 +296,9 @@ int mxg_mv_num_cols(const mxg_mv* mv) { return mv ? mv->ncols : -1; }
 int64_t mxg_mv_local_length(const mxg_mv* mv) { return mv ? mv->ld : -1; }
 int64_t mxg_mv_global_length(const mxg_mv* mv) { return mv ? mv->map->nGlobal : -1; }
 int mxg_mv_is_complex(const mxg_mv* mv) { return mv ? int(mv->isComplex) : -1; }
+mxg_map* mxg_mv_get_map(const mxg_mv* mv) { return mv ? mv->map : nullptr; }
+mxg_map* mxg_crs_row_map(const mxg_crs* A) { return A ? A->rowMap : nullptr; }
+mxg_map* mxg_crs_domain_map(const mxg_crs* A) { return A ? A->domMap : nullptr; }
 void* mxg_mv_col_ptr(mxg_mv* mv, int j) { return (mv && j >= 0 && j < mv->ncols) ? mv->col[j] : nullptr; }
 
 int mxg_mv_upload(mxg_mv* mv, const double* host, int64_t ld) {

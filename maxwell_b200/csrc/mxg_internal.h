@@ -128,6 +128,48 @@ struct mxg_mv {
 };
 
 namespace mxg {
+struct HaloPeer {
+  int rank = -1;
+  int64_t sendCount = 0, sendOffset = 0;  // entries per column; offset into the send index list
+  int64_t recvCount = 0, recvStart = 0;   // segment of the ghost list owned by this peer
+};
+}  // namespace mxg
+
+struct mxg_crs {
+  mxg_ctx* ctx = nullptr;
+  mxg_map *rowMap = nullptr, *domMap = nullptr;
+  bool isComplex = false;
+  int64_t nRows = 0, nLoc = 0, nnz = 0;
+  int64_t gLo = 0, gHi = 0;
+  // dictionary path
+  int32_t* dRowPat = nullptr;
+  int32_t* dPatOff = nullptr;
+  void* dPat = nullptr;
+  int64_t numPats = 0, dictRows = 0, patEntries = 0;
+  // general path
+  int64_t nGen = 0, ellEntries = 0;
+  int32_t* dGenRow = nullptr;
+  int32_t* dGenLen = nullptr;
+  int64_t* dSlicePtr = nullptr;
+  int32_t* dCol = nullptr;
+  void* dVal = nullptr;
+  // rows [intBegin, intEnd) need no ghost values; general rows genIntBegin..genIntEnd lie inside it
+  int64_t intBegin = 0, intEnd = 0, genIntBegin = 0, genIntEnd = 0;
+  int64_t ghostRows = 0;
+  // halo plan
+  std::vector<mxg::HaloPeer> peers;
+  int32_t* dSendIdx = nullptr;
+  int64_t sendTotal = 0;
+  mutable void* dSendBuf = nullptr;
+  mutable void* dGhost = nullptr;
+  mutable int haloCols = 0;
+  size_t deviceBytes = 0;
+  // 1 / diagonal (0 where the diagonal is 0 or absent); only for square operators whose row
+  // and domain maps coincide -- the smoothers of the multigrid cycle use it
+  void* dInvDiag = nullptr;
+};
+
+namespace mxg {
 template <class T>
 inline ColTable<T> tableOf(const mxg_mv* mv, int first = 0, int count = -1) {
   ColTable<T> t;

@@ -46,46 +46,7 @@ struct __align__(8) PatEntry<zd> {
   int32_t pad;
 };
 
-struct Peer {
-  int rank = -1;
-  int64_t sendCount = 0, sendOffset = 0;  // entries per column; offset into send index list
-  int64_t recvCount = 0, recvStart = 0;   // segment of the ghost list owned by this peer
-};
-
-}  // namespace
-
-struct mxg_crs {
-  mxg_ctx* ctx = nullptr;
-  mxg_map *rowMap = nullptr, *domMap = nullptr;
-  bool isComplex = false;
-  int64_t nRows = 0, nLoc = 0, nnz = 0;
-  int64_t gLo = 0, gHi = 0;
-  // dictionary path
-  int32_t* dRowPat = nullptr;
-  int32_t* dPatOff = nullptr;
-  void* dPat = nullptr;
-  int64_t numPats = 0, dictRows = 0, patEntries = 0;
-  // general path
-  int64_t nGen = 0, ellEntries = 0;
-  int32_t* dGenRow = nullptr;
-  int32_t* dGenLen = nullptr;
-  int64_t* dSlicePtr = nullptr;
-  int32_t* dCol = nullptr;
-  void* dVal = nullptr;
-  // rows [intBegin, intEnd) need no ghost values; general rows genIntBegin..genIntEnd lie inside it
-  int64_t intBegin = 0, intEnd = 0, genIntBegin = 0, genIntEnd = 0;
-  int64_t ghostRows = 0;
-  // halo plan
-  std::vector<Peer> peers;
-  int32_t* dSendIdx = nullptr;
-  int64_t sendTotal = 0;
-  mutable void* dSendBuf = nullptr;
-  mutable void* dGhost = nullptr;
-  mutable int haloCols = 0;
-  size_t deviceBytes = 0;
-};
-
-namespace {
+using Peer = mxg::HaloPeer;
 
 // ---- exact (unfused) accumulation --------------------------------------------------------
 __device__ __forceinline__ void accum(double& acc, double v, double x) { acc = __dadd_rn(acc, __dmul_rn(v, x)); }
@@ -145,23 +106,26 @@ __global__ void __launch_bounds__(kBlock) k_spmm_dict(int64_t rowBegin, int64_t 
     T acc[NV];
 #pragma unroll
     for (int jj = 0; jj < NV; ++jj) acc[jj] = zeroOf<T>();
-    for (int32_t q = o; q < oe; q += kUnroll) {
-      PatEntry<T> e[kUnroll];
-      T xv[kUnroll][NV];
+    // two entries per trip, no padded loads: the kernel is bound by L1 data-pipe wavefronts
+    // (ncu: l1tex__data_pipe_lsu_wavefronts 93%), so every extra load costs time
+    int32_t q = o;
+    for (; q + 1 < oe; q += 2) {
+      const PatEntry<T> e0 = pat[q], e1 = pat[q + 1];
+      T x0[NV], x1[NV];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) e[u] = pat[min(q + u, oe - 1)];
+      for (int jj = 0; jj < NV; ++jj) {
+        x0[jj] = loadX<T, GHOST>(X, min(j0 + jj, nvec - 1), row + e0.d);
+        x1[jj] = loadX<T, GHOST>(X, min(j0 + jj, nvec - 1), row + e1.d);
+      }
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u)
+      for (int jj = 0; jj < NV; ++jj) accum(acc[jj], entryVal(e0), x0[jj]);
 #pragma unroll
-        for (int jj = 0; jj < NV; ++jj)
-          xv[u][jj] = loadX<T, GHOST>(X, min(j0 + jj, nvec - 1), row + e[u].d);
+      for (int jj = 0; jj < NV; ++jj) accum(acc[jj], entryVal(e1), x1[jj]);
+    }
+    if (q < oe) {
+      const PatEntry<T> e0 = pat[q];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u)
-        if (q + u < oe) {
-          const T v = entryVal(e[u]);
-#pragma unroll
-          for (int jj = 0; jj < NV; ++jj) accum(acc[jj], v, xv[u][jj]);
-        }
+      for (int jj = 0; jj < NV; ++jj) accum(acc[jj], entryVal(e0), loadX<T, GHOST>(X, min(j0 + jj, nvec - 1), row + e0.d));
     }
 #pragma unroll
     for (int jj = 0; jj < NV; ++jj)
@@ -624,6 +588,31 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
   T* dVal = nullptr;
   if ((rc = uploadVec(ellVal, &dVal, &A->deviceBytes, ctx))) return rc;
   A->dVal = dVal;
+  // inverse diagonal for the smoothers (square operators on a single map only)
+  if (nRows == nLoc && A->rowMap->gids == A->domMap->gids) {
+    std::vector<T> inv(nRows, zeroOf<T>());
+    for (int64_t r = 0; r < nRows; ++r)
+      for (int64_t k = rp[r]; k < rp[r + 1]; ++k)
+        if (ext[k] == r) {
+          const T d = val[k];
+          if (!isZero(d)) {
+            if constexpr (sizeof(T) == sizeof(double)) {
+              double dd; std::memcpy(&dd, &d, sizeof(double));
+              dd = 1.0 / dd;
+              std::memcpy(&inv[r], &dd, sizeof(double));
+            } else {
+              double re, im; std::memcpy(&re, &d, sizeof(double)); std::memcpy(&im, reinterpret_cast<const char*>(&d) + 8, 8);
+              const double m2 = re * re + im * im;
+              const double o[2] = {re / m2, -im / m2};
+              std::memcpy(&inv[r], o, 16);
+            }
+          }
+        }
+    T* dInv = nullptr;
+    size_t unused = 0;
+    if ((rc = uploadVec(inv, &dInv, &unused, ctx))) return rc;
+    A->dInvDiag = dInv;
+  }
   return MXG_OK;
 }
 
@@ -671,7 +660,7 @@ int mxg_crs_destroy(mxg_crs* A) {
   cudaSetDevice(A->ctx->device);
   cudaStreamSynchronize(A->ctx->stream);
   cudaStreamSynchronize(A->ctx->commStream);
-  void* ptrs[] = {A->dRowPat, A->dPatOff, A->dPat, A->dGenRow, A->dGenLen, A->dSlicePtr, A->dCol, A->dVal, A->dSendIdx, A->dSendBuf, A->dGhost};
+  void* ptrs[] = {A->dRowPat, A->dPatOff, A->dPat, A->dGenRow, A->dGenLen, A->dSlicePtr, A->dCol, A->dVal, A->dSendIdx, A->dSendBuf, A->dGhost, A->dInvDiag};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   mxg_map_destroy(A->rowMap);

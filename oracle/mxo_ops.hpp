@@ -313,6 +313,88 @@ void spmm(const Csr<S>& A, const S* X, int64_t ldx, S* Y, int64_t ldy, int nvec)
   }
 }
 
+// MxGridFieldInterpolator.cpp:28-65 (stencil), :68-122 (insertion, row-sum normalisation):
+// (tri)linear interpolation of `from` at the component positions of `to`. Entries whose
+// column is not in the from-map are dropped, then every row is divided by the sum of the
+// magnitudes of what is left. Two latent bugs of the reference are NOT reproduced: the
+// stencil weights use an unset point `p` (:39,60 -- we use the target position) and
+// getRowSums never zeroes its accumulator (MxCrsMatrix.cpp:306-310); see DESIGN.md R12.
+template <class S>
+Csr<S> interpolator(const Field& from, const Field& to) {
+  if (from.ncomp != to.ncomp) throw std::runtime_error("mxo: interpolator needs fields with equal component counts");
+  Csr<S> m;
+  startMatrix(m, to, from);
+  const Grid& fg = *from.g;
+  RowBuf<S> row;
+  for (int64_t gid : to.gids) {
+    I3 tcell; int comp;
+    cellCompOf(to, gid, tcell, comp);
+    const D3 point = to.g->nodeCoord(tcell) + to.xi[comp];
+    I3 c0;
+    for (int i = 0; i < 3; ++i)
+      c0[i] = int(std::floor((point[i] - from.xi[comp][i] - fg.origin[i]) / fg.d[i]));
+    double sum = 0.0;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 2; ++c) {
+          const I3 cell{c0[0] + a, c0[1] + b, c0[2] + c};
+          const D3 p0 = fg.nodeCoord(cell) + from.xi[comp];
+          double w = 1.0;
+          for (int i = 0; i < 3; ++i) w *= 1.0 - std::fabs(point[i] - p0[i]) / fg.d[i];
+          // cells outside the guarded block cannot be interiorised meaningfully; skip them
+          bool inRange = true;
+          for (int i = 0; i < 3; ++i)
+            if (cell[i] < -1 || cell[i] > fg.N[i] + 1) inRange = false;
+          if (!inRange) continue;
+          const int64_t cg = from.gid(comp, cell);
+          const int32_t l = from.lid(cg);
+          if (l < 0) continue;
+          row.add(l, S(w));
+          sum += std::fabs(w);
+        }
+    if (sum > 0)
+      for (auto& e : row.e) e.second = e.second / S(sum);
+    row.flushInto(m);
+  }
+  return m;
+}
+
+template <class S> inline S conjOf(const S& v);
+template <> inline double conjOf<double>(const double& v) { return v; }
+template <> inline cplx conjOf<cplx>(const cplx& v) { return std::conj(v); }
+
+// (conjugate) transpose, rows sorted by column
+template <class S>
+Csr<S> transpose(const Csr<S>& A) {
+  Csr<S> T;
+  T.nrows = A.ncols; T.ncols = A.nrows;
+  T.rowGid = A.colGid; T.colGid = A.rowGid;
+  T.rowptr.assign(T.nrows + 1, 0);
+  for (int64_t p = 0; p < A.nnz(); ++p) T.rowptr[A.col[p] + 1]++;
+  for (int64_t i = 0; i < T.nrows; ++i) T.rowptr[i + 1] += T.rowptr[i];
+  T.col.resize(A.nnz());
+  T.val.resize(A.nnz());
+  std::vector<int64_t> fill(T.rowptr.begin(), T.rowptr.end() - 1);
+  for (int64_t i = 0; i < A.nrows; ++i)
+    for (int64_t p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) {
+      const int64_t o = fill[A.col[p]]++;
+      T.col[o] = int32_t(i);
+      T.val[o] = conjOf(A.val[p]);
+    }
+  return T;
+}
+
+// divide every row by the sum of the magnitudes of its entries (rows of zeros stay empty)
+template <class S>
+void normalizeRows(Csr<S>& A) {
+  for (int64_t i = 0; i < A.nrows; ++i) {
+    double sum = 0;
+    for (int64_t p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) sum += std::abs(A.val[p]);
+    if (sum > 0)
+      for (int64_t p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) A.val[p] = A.val[p] / S(sum);
+  }
+}
+
 // The reference's storage for complex scalars: real 2n x 2n "K form" with interleaved
 // re/im rows and the 2x2 block [[a,-b],[b,a]] per entry (MxCrsMatrix.cpp:145-170,
 // MxMap.cpp:90-108).

@@ -136,6 +136,44 @@ void* mxo_mat_multiply(void* a, void* b) {
   if (rc != 0) { delete m; return nullptr; }
   return m;
 }
+// interpolation of field `field` of simFrom at the component positions of simTo
+// (MxGridFieldInterpolator; the refiners / coarseners of MxGeoMultigridPrec.cpp:438-452)
+void* mxo_build_interp(void* simFrom, void* simTo, const char* field, int is_complex) {
+  Mat* m = new Mat;
+  m->cplx_ = is_complex != 0;
+  const int rc = guard([&] {
+    const Field* f = fieldOf(static_cast<Sim*>(simFrom), field);
+    const Field* t = fieldOf(static_cast<Sim*>(simTo), field);
+    if (m->cplx_) m->c = interpolator<cplx>(*f, *t); else m->r = interpolator<double>(*f, *t);
+  });
+  if (rc != 0) { delete m; return nullptr; }
+  return m;
+}
+void* mxo_mat_transpose(void* h, int normalize_rows) {
+  Mat* src = static_cast<Mat*>(h);
+  Mat* m = new Mat;
+  m->cplx_ = src->cplx_;
+  if (src->cplx_) { m->c = transpose(src->c); if (normalize_rows) normalizeRows(m->c); }
+  else { m->r = transpose(src->r); if (normalize_rows) normalizeRows(m->r); }
+  return m;
+}
+// C = sa*A + sb*B (EpetraExt::MatrixMatrix::Add semantics; shifted operators, MxMagWaveOp.cpp:247-256)
+void* mxo_mat_add(void* a, const double sa[2], void* b, const double sb[2]) {
+  Mat *A = static_cast<Mat*>(a), *B = static_cast<Mat*>(b);
+  Mat* m = new Mat;
+  m->cplx_ = A->cplx_;
+  const int rc = guard([&] {
+    if (A->cplx_ != B->cplx_) throw std::runtime_error("mxo: mixed scalar types");
+    if (A->cplx_) m->c = add(A->c, cplx(sa[0], sa[1]), B->c, cplx(sb[0], sb[1]));
+    else m->r = add(A->r, sa[0], B->r, sb[0]);
+  });
+  if (rc != 0) { delete m; return nullptr; }
+  return m;
+}
+void mxo_mat_scale(void* h, const double s[2]) {
+  Mat* m = static_cast<Mat*>(h);
+  if (m->cplx_) scaleInPlace(m->c, cplx(s[0], s[1])); else scaleInPlace(m->r, s[0]);
+}
 void mxo_mat_destroy(void* h) { delete static_cast<Mat*>(h); }
 int mxo_mat_is_complex(void* h) { return static_cast<Mat*>(h)->cplx_ ? 1 : 0; }
 void mxo_mat_shape(void* h, int64_t* nrows, int64_t* ncols, int64_t* nnz) {

@@ -54,6 +54,10 @@ def lib():
             "mxo_build_op": (vp, [vp, cp, C.c_int]),
             "mxo_mat_kform": (vp, [vp]),
             "mxo_mat_multiply": (vp, [vp, vp]),
+            "mxo_build_interp": (vp, [vp, vp, cp, C.c_int]),
+            "mxo_mat_transpose": (vp, [vp, C.c_int]),
+            "mxo_mat_add": (vp, [vp, d3, vp, d3]),
+            "mxo_mat_scale": (None, [vp, d3]),
             "mxo_mat_destroy": (None, [vp]),
             "mxo_mat_is_complex": (C.c_int, [vp]),
             "mxo_mat_shape": (None, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
@@ -170,6 +174,22 @@ class Matrix:
             raise RuntimeError(lib().mxo_last_error().decode())
         return Matrix(h)
 
+    def transpose(self, normalize_rows=False, scale=None):
+        """(conjugate) transpose, optionally row-normalised or multiplied by `scale`."""
+        m = Matrix(lib().mxo_mat_transpose(self.h, int(normalize_rows)))
+        if scale is not None:
+            s = complex(scale)
+            lib().mxo_mat_scale(m.h, (C.c_double * 2)(s.real, s.imag))
+        return m
+
+    def add(self, sa, other, sb):
+        """sa*self + sb*other on the union pattern."""
+        sa, sb = complex(sa), complex(sb)
+        h = lib().mxo_mat_add(self.h, (C.c_double * 2)(sa.real, sa.imag), other.h, (C.c_double * 2)(sb.real, sb.imag))
+        if not h:
+            raise RuntimeError(lib().mxo_last_error().decode())
+        return Matrix(h)
+
     def __matmul__(self, other):
         h = lib().mxo_mat_multiply(self.h, other.h)
         if not h:
@@ -233,6 +253,15 @@ class Sim:
             lib().mxo_sim_destroy(self.h)
         except Exception:
             pass
+
+
+def interpolator(sim_from, sim_to, field="bfield", is_complex=False):
+    """Trilinear interpolation of `field` from sim_from's grid to sim_to's component positions
+    (MxGridFieldInterpolator.cpp:28-122): the refiners/coarseners of the multigrid spec."""
+    h = lib().mxo_build_interp(sim_from.h, sim_to.h, field.encode(), int(is_complex))
+    if not h:
+        raise RuntimeError(lib().mxo_last_error().decode())
+    return Matrix(h)
 
 
 def csr_apply(rowptr, col, val, X, nthreads=0):

@@ -1,0 +1,105 @@
+"""GPU eigensolve parity: MxSolver (LOBPCG through the MxAnasaziMV / Operator surface) and the multigrid
+preconditioner vs scipy on the oracle-generated operators. Bar (north_star): eigenvalues within 1e-9 relative,
+matching mode count, residuals below the solver tolerance."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as sla
+
+from conftest import gpu_matrix, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _hierarchy(mx, ctx, orc, make_sim, sizes, name="vecLapl"):
+    sims = [make_sim(n) for n in sizes]
+    ops, maps = [], []
+    for s in sims:
+        A, op, rmap, _ = gpu_matrix(mx, ctx, s, name)
+        ops.append(A)
+        maps.append(rmap)
+    R, P = [], []
+    for l in range(len(sims) - 1):
+        p = orc.interpolator(sims[l + 1], sims[l])        # coarse -> fine (refiner, MxGridFieldInterpolator)
+        # fine -> coarse: P^T / 2^d. The reference spec interpolates in both directions
+        # (MxGeoMultigridPrec.cpp:438-452), which diverges on cut-cell operators (GMG notes).
+        r = p.transpose(scale=1.0 / 8.0)
+        for mat, rm, cm, out in ((p, maps[l], maps[l + 1], P), (r, maps[l + 1], maps[l], R)):
+            rowptr, col, val = mat.arrays()
+            _, cg = mat.maps()
+            out.append(mx.MxCrsMatrix.from_csr(rm, cm, rowptr, cg[col], val))
+    return sims, ops, maps, R, P
+
+
+def test_vcycle_reduces_residual(mx, ctx, orc):
+    sims, ops, maps, R, P = _hierarchy(mx, ctx, orc, orc.pillbox, [32, 16, 8])
+    prec = mx.MxGeoMultigridPrec(ctx, ops, R, P, smoother_sweeps=2, cycles=1)
+    assert prec.nlevels == 3 and prec.info(0)["lambda_max"] > 1.0
+    op = sims[0].op("vecLapl")
+    fa = sims[0].fracs("bfield")
+    rng = np.random.default_rng(0)
+    xs = rng.standard_normal((op.nrows, 2)) * (fa > 0)[:, None]
+    b = mx.MxMultiVector(maps[0], 2)
+    x = mx.MxMultiVector(maps[0], 2)
+    b.from_host(op.apply(xs))
+    # stationary iteration x <- x + M^-1 (b - A x): the error must contract every cycle
+    r = mx.MxMultiVector(maps[0], 2)
+    e = mx.MxMultiVector(maps[0], 2)
+    norms = [b.norm2().max()]
+    for _ in range(6):
+        r.assign(b)
+        ops[0].apply_axpby(-1.0, x, 1.0, r)
+        prec.ApplyInverse(r, e)
+        x.MvAddMv(1.0, x, 1.0, e)
+        r.assign(b)
+        ops[0].apply_axpby(-1.0, x, 1.0, r)
+        norms.append(r.norm2().max())
+    rates = [norms[i + 1] / norms[i] for i in range(len(norms) - 1)]
+    assert max(rates) < 0.7, rates           # V(2,2) Chebyshev cycle on the cut-cell vector Laplacian: ~0.6
+    assert norms[-1] < 0.05 * norms[0]
+
+
+def test_vacuum_lowest_modes_analytic(mx, ctx, orc):
+    """Periodic vacuum box: lambda = sum_i (2/h sin(pi m_i/N))^2; vecLapl has each 3-fold (plus constants)."""
+    N = 16
+    A, op, rmap, _ = gpu_matrix(mx, ctx, orc.vacuum(N), "vecLapl")
+    s = mx.MxSolver(ctx, A, nev=9, block_size=24, tol=1e-9, max_iters=400)
+    ev = s.solve()
+    lam = (2 * N * np.sin(np.pi / N)) ** 2
+    ref = np.array([0.0] * 3 + [lam] * 6)
+    assert s.converged == 9
+    np.testing.assert_allclose(ev[3:], ref[3:], rtol=1e-9)
+    assert np.all(np.abs(ev[:3]) < 1e-6)
+
+
+@pytest.mark.parametrize("use_prec", [False, True])
+def test_pillbox_eigenvalues_match_scipy(mx, ctx, orc, use_prec):
+    sizes = [24, 12, 6] if use_prec else [24]
+    sims, ops, maps, R, P = _hierarchy(mx, ctx, orc, orc.pillbox, sizes)
+    sim = sims[0]
+    fa = sim.fracs("bfield")
+    md = mx.MxMultiVector(maps[0], 1)
+    md.from_host(fa)
+    prec = mx.MxGeoMultigridPrec(ctx, ops, R, P, smoother_sweeps=2) if use_prec else None
+    nev = 10
+    s = mx.MxSolver(ctx, ops[0], m_diag=md, prec=prec, nev=nev, block_size=20, tol=1e-9, max_iters=1500 if not use_prec else 300)
+    ev = s.solve()
+    assert s.converged == nev, (s.converged, s.residuals)
+    # reference: scipy shift-invert on the same pencil restricted to DOFs with positive area
+    Asp, keep = sim.op("vecLapl").scipy(), np.where(fa > 0)[0]
+    ref = sla.eigsh(Asp[keep][:, keep].tocsc(), k=nev + 4, M=sp.diags(fa[keep]).tocsc(), sigma=-1.0, which="LM", tol=1e-13,
+                    return_eigenvectors=False)
+    ref = np.sort(ref)[:nev]
+    big = ref > 1e-6
+    np.testing.assert_allclose(ev[big], ref[big], rtol=1e-9)
+    assert np.all(np.abs(ev[~big]) < 1e-6)
+    res, div = s.check()
+    assert np.all(res[:nev][big] < 1e-6)                       # the reference's own acceptance test (default tol 1e-6)
+    if use_prec:
+        assert s.iterations < 60, s.iterations
+    # Maxwell modes are the divergence-free ones: TM010 must be among them at ~ (2.405/R)^2
+    D, _, _, _ = gpu_matrix(mx, ctx, sim, "divB")
+    _, div = s.check(D)
+    maxwell = ev[(div[:nev] < 1e-6) & big]
+    assert len(maxwell) >= 1
+    assert abs(maxwell[0] - (2.405 / 0.4) ** 2) < 0.8
