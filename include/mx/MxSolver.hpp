@@ -228,12 +228,14 @@ struct MxSolverParams {
   int verbose = 0;
   uint64_t seed = 12345;
   bool randomInit = true;  // MxSolver.cpp:62-64 starts from MvRandom
+  bool profile = false;    // per-phase wall times (synchronises around each phase)
 };
 
 struct MxSolverResult {
   std::vector<double> eigenvalues, residuals;   // blockSize entries, ascending
   int iterations = 0, converged = 0;
   long applyA = 0, applyPrec = 0;
+  double tApplyA = 0, tPrec = 0, tGram = 0, tUpdate = 0;   // filled when params.profile is set (adds syncs)
   double seconds = 0.0;
 };
 
@@ -263,20 +265,30 @@ class MxSolver {
     MV Sb(map, 3 * m), ASb(map, 3 * m), MSb(map, 3 * m), tmp(map, 2 * m);
     auto range = [](int b, int n) { std::vector<int> v(n); std::iota(v.begin(), v.end(), b); return v; };
     auto view = [&](MV& base, const std::vector<int>& cols) { return std::unique_ptr<MV>(static_cast<MV*>(base.CloneViewNonConst(cols))); };
+    auto timeit = [&](double& acc, auto&& f) {
+      if (!p_.profile) { f(); return; }
+      map->getComm()->sync();
+      const auto a = clock::now();
+      f();
+      map->getComm()->sync();
+      acc += std::chrono::duration<double>(clock::now() - a).count();
+    };
     auto applyM = [&](const MV& in, MV& out) { if (M_) M_->Apply(in, out); else out = in; };
     auto rightMul = [&](MV& base, const std::vector<int>& srcCols, const Dense& C, const std::vector<int>& dstCols) {
       // base(:, dstCols) = base(:, srcCols) * C  through the temp block (src and dst may overlap)
-      auto src = view(base, srcCols);
-      auto t = view(tmp, range(0, C.numCols()));
-      t->MvTimesMatAddMv(1.0, *src, C, 0.0);
-      auto dst = view(base, dstCols);
-      *dst = *t;
+      timeit(res.tUpdate, [&] {
+        auto src = view(base, srcCols);
+        auto t = view(tmp, range(0, C.numCols()));
+        t->MvTimesMatAddMv(1.0, *src, C, 0.0);
+        auto dst = view(base, dstCols);
+        *dst = *t;
+      });
     };
     auto gram = [&](MV& left, const std::vector<int>& lc, MV& right, const std::vector<int>& rc) {
       auto l = view(left, lc);
       auto r = view(right, rc);
       Dense G(int(lc.size()), int(rc.size()));
-      r->MvTransMv(1.0, *l, G);
+      timeit(res.tGram, [&] { r->MvTransMv(1.0, *l, G); });
       return G;
     };
     auto toVec = [](const Dense& G) { return std::vector<double>(G.values(), G.values() + size_t(G.numRows()) * G.numCols()); };
@@ -337,7 +349,7 @@ class MxSolver {
     {
       auto x = view(Sb, xc);
       auto ax = view(ASb, xc);
-      A_->Apply(*x, *ax);
+      timeit(res.tApplyA, [&] { A_->Apply(*x, *ax); });
       res.applyA += m;
     }
     std::vector<double> theta(m, 0.0);
@@ -398,7 +410,7 @@ class MxSolver {
       {  // W = T R(:, active)
         auto Ra = view(tmp, active);
         auto W = view(Sb, wc);
-        if (T_) { T_->Apply(*Ra, *W); res.applyPrec += na; }
+        if (T_) { timeit(res.tPrec, [&] { T_->Apply(*Ra, *W); }); res.applyPrec += na; }
         else *W = *Ra;
         auto MW = view(MSb, wc);
         applyM(*W, *MW);
@@ -413,7 +425,7 @@ class MxSolver {
       if (!wc.empty()) {
         auto W = view(Sb, wc);
         auto AW = view(ASb, wc);
-        A_->Apply(*W, *AW);
+        timeit(res.tApplyA, [&] { A_->Apply(*W, *AW); });
         res.applyA += long(wc.size());
       }
       np = orthonormalize(pc, true);             // a degenerate search block shrinks or disappears
@@ -452,7 +464,7 @@ class MxSolver {
       sc.insert(sc.end(), wc.begin(), wc.end());
       if (np > 0) { const std::vector<int> pcc = range(2 * m, np); sc.insert(sc.end(), pcc.begin(), pcc.end()); wpc.insert(wpc.end(), pcc.begin(), pcc.end()); }
       const std::vector<int> pnew = range(2 * m, m);
-      for (MV* base : {&Sb, &ASb, &MSb}) {
+      for (MV* base : {&Sb, &ASb, &MSb}) timeit(res.tUpdate, [&] {
         auto s = view(*base, sc);
         auto wp = view(*base, wpc);
         auto tx = view(tmp, range(0, m));
@@ -463,7 +475,7 @@ class MxSolver {
         auto pdst = view(*base, pnew);
         *xdst = *tx;
         *pdst = *tp;
-      }
+      });
       np = m;
       for (int j = 0; j < m; ++j) theta[j] = w[j];
     }

@@ -20,6 +20,9 @@ typedef struct mxs_params {
 
 void mxs_default_params(mxs_params* p);
 const char* mxs_last_error(void);
+/* per-phase seconds of the last mxs_lobpcg call made with verbose >= 2 (which synchronises around phases):
+ * out[0]=operator applies, [1]=preconditioner, [2]=Gram products, [3]=basis updates */
+void mxs_last_profile(double out[4]);
 /* A: assembled operator (curlCurl or vecLapl); m_diag: one-column multivector holding the diagonal
  * of the mass matrix mRhs (NULL = identity); prec: multigrid preconditioner (NULL = none).
  * X: n x block multivector, receives the M-orthonormal Ritz vectors.

@@ -8,6 +8,7 @@
 
 namespace {
 thread_local std::string g_err;
+thread_local double g_profile[4] = {0, 0, 0, 0};
 struct Wrapped {
   std::shared_ptr<MxComm> comm;
   std::shared_ptr<MxMap> map;
@@ -35,6 +36,7 @@ void mxs_default_params(mxs_params* p) {
 }
 
 const char* mxs_last_error(void) { return g_err.c_str(); }
+void mxs_last_profile(double out[4]) { for (int i = 0; i < 4; ++i) out[i] = g_profile[i]; }
 
 int mxs_lobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, mxg_mv* X, const mxs_params* p,
                double* evals, double* resnorms, int64_t info[4], double* seconds) {
@@ -56,6 +58,7 @@ int mxs_lobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, mxg_mv* 
     sp.verbose = p->verbose;
     sp.seed = p->seed;
     sp.randomInit = p->random_init != 0;
+    sp.profile = p->verbose >= 2;
     MxSolver solver(&Aop, Mop.get(), Top.get(), sp);
     MxSolverResult r = solver.solve(Xmv);
     const int m = sp.blockSize;
@@ -63,6 +66,7 @@ int mxs_lobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, mxg_mv* 
     if (resnorms) std::memcpy(resnorms, r.residuals.data(), sizeof(double) * m);
     if (info) { info[0] = r.iterations; info[1] = r.converged; info[2] = r.applyA; info[3] = r.applyPrec; }
     if (seconds) *seconds = r.seconds;
+    g_profile[0] = r.tApplyA; g_profile[1] = r.tPrec; g_profile[2] = r.tGram; g_profile[3] = r.tUpdate;
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();

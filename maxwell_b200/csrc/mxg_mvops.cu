@@ -174,6 +174,70 @@ __global__ void __launch_bounds__(kBlock) k_trans_mv(ColTable<T> A, int k, ColTa
     }
 }
 
+// Real-valued Gram product with shared-memory staging: one block owns a 64 x 64 tile of C and
+// streams rows in chunks of kGramRows. Each chunk of the (up to) 64 A-columns and 64 X-columns is
+// loaded ONCE from global memory (coalesced, one column per warp-load) into shared memory and then
+// reused by all 256 threads, each of which keeps a 4 x 4 register tile of C. Column ownership is
+// interleaved (thread (ty, tx) owns A-columns ty + 16 i and X-columns tx + 16 j) and the shared
+// column stride is odd in 8-byte words, so every shared load is conflict-free or a broadcast.
+constexpr int kGramRows = 32;
+constexpr int kGramStride = kGramRows + 1;
+// RI x RJ = per-thread register tile; the block tile of C is (16 RI) x (16 RJ)
+template <int RI, int RJ>
+__global__ void __launch_bounds__(kBlock, 2) k_gram_tiled(ColTable<double> A, int k, ColTable<double> X, int b, int64_t n,
+                                                          int tilesB, double* __restrict__ partial /* [k*b][gridDim.y] */) {
+  constexpr int TI = 16 * RI, TJ = 16 * RJ;
+  __shared__ double sA[TI * kGramStride];
+  __shared__ double sX[TJ * kGramStride];
+  const int tk = blockIdx.x / tilesB, tb = blockIdx.x % tilesB;
+  const int k0 = tk * TI, b0 = tb * TJ;
+  const int kc = min(TI, k - k0), bc = min(TJ, b - b0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  double acc[RI][RJ];
+#pragma unroll
+  for (int i = 0; i < RI; ++i)
+#pragma unroll
+    for (int j = 0; j < RJ; ++j) acc[i][j] = 0.0;
+  const int64_t chunks = (n + kGramRows - 1) / kGramRows;
+  for (int64_t ch = blockIdx.y; ch < chunks; ch += gridDim.y) {
+    const int64_t r = ch * kGramRows + lane;
+    const bool ok = r < n;
+    // warp w stages columns w, w+8, ... of both operands; lane = row inside the chunk
+#pragma unroll
+    for (int c = 0; c < TI / 8; ++c) {
+      const int col = warp + 8 * c;
+      sA[col * kGramStride + lane] = (ok && col < kc) ? A.p[k0 + col][r] : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < TJ / 8; ++c) {
+      const int col = warp + 8 * c;
+      sX[col * kGramStride + lane] = (ok && col < bc) ? X.p[b0 + col][r] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < kGramRows; ++rr) {
+      double av[RI], xv[RJ];
+#pragma unroll
+      for (int i = 0; i < RI; ++i) av[i] = sA[(ty + 16 * i) * kGramStride + rr];
+#pragma unroll
+      for (int j = 0; j < RJ; ++j) xv[j] = sX[(tx + 16 * j) * kGramStride + rr];
+#pragma unroll
+      for (int i = 0; i < RI; ++i)
+#pragma unroll
+        for (int j = 0; j < RJ; ++j) acc[i][j] = fma(av[i], xv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < RI; ++i)
+#pragma unroll
+    for (int j = 0; j < RJ; ++j) {
+      const int ci = ty + 16 * i, cj = tx + 16 * j;
+      if (ci < kc && cj < bc) partial[(int64_t(k0 + ci) + int64_t(b0 + cj) * k) * gridDim.y + blockIdx.y] = acc[i][j];
+    }
+}
+
 // ---- tall-skinny update: Y = alpha * A * B + beta * Y ---------------------------------------
 // The small dense B rides in the kernel parameter block (constant bank): the FMAs take it as a
 // uniform operand, so the only memory instructions are the streaming loads of A and Y.
@@ -184,26 +248,54 @@ struct DenseParam {
 __device__ inline double denseAt(const DenseParam& B, int idx, double) { return B.v[idx]; }
 __device__ inline zd denseAt(const DenseParam& B, int idx, zd) { return {B.v[2 * idx], B.v[2 * idx + 1]}; }
 
-template <class T, int BT>
+// B (k x bcount) is copied from the parameter block into shared memory as [i][j] (j fastest), so
+// the inner loop reads it with warp-wide broadcast loads; every thread owns RT rows x BT columns of
+// the result in registers (one B value feeds RT FMAs, one A value feeds BT FMAs).
+template <class T, int BT, int RT>
 __global__ void __launch_bounds__(kBlock) k_times_mat(ColTable<T> A, int k, const __grid_constant__ DenseParam B, int b0, int bcount,
                                                       T alpha, T beta, bool useY, ColTable<T> Y, int64_t n) {
-  for (int64_t r = blockIdx.x * int64_t(kBlock) + threadIdx.x; r < n; r += int64_t(gridDim.x) * kBlock) {
-    T acc[BT];
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  T* sB = reinterpret_cast<T*>(smemRaw);   // [k][BT]
+  for (int t = threadIdx.x; t < k * BT; t += kBlock) {
+    const int i = t / BT, j = t % BT;
+    sB[t] = j < bcount ? denseAt(B, i + (b0 + j) * k, T()) : zeroOf<T>();
+  }
+  __syncthreads();
+  const int64_t tile = int64_t(kBlock) * RT;
+  for (int64_t base = blockIdx.x * tile; base < n; base += int64_t(gridDim.x) * tile) {
+    int64_t r[RT];
+    bool ok[RT];
 #pragma unroll
-    for (int j = 0; j < BT; ++j) acc[j] = zeroOf<T>();
+    for (int t = 0; t < RT; ++t) { r[t] = base + t * kBlock + threadIdx.x; ok[t] = r[t] < n; if (!ok[t]) r[t] = n - 1; }
+    T acc[RT][BT];
+#pragma unroll
+    for (int t = 0; t < RT; ++t)
+#pragma unroll
+      for (int j = 0; j < BT; ++j) acc[t][j] = zeroOf<T>();
+#pragma unroll 2
     for (int i = 0; i < k; ++i) {
-      const T a = A.p[i][r];
+      T a[RT];
+      const T* col = A.p[i];
 #pragma unroll
-      for (int j = 0; j < BT; ++j)
-        if (j < bcount) fmaInto(acc[j], a, denseAt(B, i + (b0 + j) * k, T()));
+      for (int t = 0; t < RT; ++t) a[t] = col[r[t]];
+#pragma unroll
+      for (int j = 0; j < BT; ++j) {
+        const T bv = sB[i * BT + j];
+#pragma unroll
+        for (int t = 0; t < RT; ++t) fmaInto(acc[t][j], a[t], bv);
+      }
     }
 #pragma unroll
     for (int j = 0; j < BT; ++j)
       if (j < bcount) {
         T* y = Y.p[b0 + j];
-        T v = alpha * acc[j];
-        if (useY) v = v + beta * y[r];
-        y[r] = v;
+#pragma unroll
+        for (int t = 0; t < RT; ++t)
+          if (ok[t]) {
+            T v = alpha * acc[t][j];
+            if (useY) v = v + beta * y[r[t]];
+            y[r[t]] = v;
+          }
       }
   }
 }
@@ -306,11 +398,36 @@ int transMvImpl(const double alpha[2], const mxg_mv* A, const mxg_mv* X, double*
   if (slices > maxSlices) slices = maxSlices;
   if (slices < 1) slices = 1;
   const size_t kb = size_t(k) * b;
+  // shared-memory tiled kernel (real case): the block tile of C is (16 ri) x (16 rj) with ri, rj in 1..4
+  // chosen to cover k and b with as little padding as possible
+  const int ri = k >= 49 ? 4 : (k + 15) / 16, rj = b >= 49 ? 4 : (b + 15) / 16;
+  const int gtB = (b + 16 * rj - 1) / (16 * rj), gtiles = ((k + 16 * ri - 1) / (16 * ri)) * gtB;
+  int gs = (ctx->numSMs * 2 + gtiles - 1) / gtiles;
+  {
+    const int64_t chunks = (A->ld + kGramRows - 1) / kGramRows;
+    if (gs > chunks) gs = int(chunks);
+    if (gs < 1) gs = 1;
+  }
+  if (w == 1) slices = gs;
   int rc = ensureScratch(ctx, sizeof(T) * (kb * slices + kb));
   if (rc) return rc;
   T* out = reinterpret_cast<T*>(ctx->dScratch);
   T* partial = out + kb;
-  k_trans_mv<T, KT, BT><<<dim3(tiles, slices), kBlock, 0, ctx->stream>>>(tableOf<T>(A), k, tableOf<T>(X), b, A->ld, tilesB, partial);
+  if constexpr (w == 1) {
+    const dim3 grid(gtiles, gs);
+    auto ta = tableOf<double>(A), tx = tableOf<double>(X);
+    double* part = reinterpret_cast<double*>(partial);
+#define MXG_GRAM(RI, RJ) k_gram_tiled<RI, RJ><<<grid, kBlock, 0, ctx->stream>>>(ta, k, tx, b, A->ld, gtB, part)
+    switch (ri * 4 + rj) {
+      case 5: MXG_GRAM(1, 1); break;  case 6: MXG_GRAM(1, 2); break;  case 7: MXG_GRAM(1, 3); break;  case 8: MXG_GRAM(1, 4); break;
+      case 9: MXG_GRAM(2, 1); break;  case 10: MXG_GRAM(2, 2); break; case 11: MXG_GRAM(2, 3); break; case 12: MXG_GRAM(2, 4); break;
+      case 13: MXG_GRAM(3, 1); break; case 14: MXG_GRAM(3, 2); break; case 15: MXG_GRAM(3, 3); break; case 16: MXG_GRAM(3, 4); break;
+      case 17: MXG_GRAM(4, 1); break; case 18: MXG_GRAM(4, 2); break; case 19: MXG_GRAM(4, 3); break; default: MXG_GRAM(4, 4); break;
+    }
+#undef MXG_GRAM
+  } else {
+    k_trans_mv<T, KT, BT><<<dim3(tiles, slices), kBlock, 0, ctx->stream>>>(tableOf<T>(A), k, tableOf<T>(X), b, A->ld, tilesB, partial);
+  }
   LAUNCH_CHECK(ctx);
   k_reduce_partials<T><<<int(kb), kBlock, 0, ctx->stream>>>(partial, slices, out);
   LAUNCH_CHECK(ctx);
@@ -332,14 +449,16 @@ int timesMatImpl(const double alpha[2], const mxg_mv* A, const double* B, int ld
   mxg_ctx* ctx = A->map->ctx;
   if (Y->ld == 0) return MXG_OK;
   constexpr int w = sizeof(T) / sizeof(double);
-  constexpr int BT = (w == 1) ? 8 : 4;
+  constexpr int BT = (w == 1) ? 16 : 8;   // output columns per pass over A (accumulators stay in registers)
+  constexpr int RT = 2;                     // rows per thread
   const int k = A->ncols, b = Y->ncols;
   const T al = scalarOf<T>(alpha), be = scalarOf<T>(beta);
   const bool useY = !isZero(be);
   // columns of B that fit in one parameter block
   const int colsPerLaunch = kMaxBParam / (k * w);
   MXG_REQUIRE(colsPerLaunch >= 1, "mxg_mv_times_mat_add_mv: A has too many columns (%d) for one pass", k);
-  const int grid = gridFor(ctx, Y->ld, kBlock, 8);
+  const int grid = gridFor(ctx, Y->ld, kBlock * RT, 4);
+  const size_t smem = sizeof(T) * size_t(k) * BT;
   for (int c0 = 0; c0 < b; c0 += colsPerLaunch) {
     const int cc = (b - c0 < colsPerLaunch) ? b - c0 : colsPerLaunch;
     DenseParam P;
@@ -349,7 +468,7 @@ int timesMatImpl(const double alpha[2], const mxg_mv* A, const double* B, int ld
     ColTable<T> ty = tableOf<T>(Y, c0, cc);
     for (int j0 = 0; j0 < cc; j0 += BT) {
       const int bc = (cc - j0 < BT) ? cc - j0 : BT;
-      k_times_mat<T, BT><<<grid, kBlock, 0, ctx->stream>>>(tableOf<T>(A), k, P, j0, bc, al, be, useY, ty, Y->ld);
+      k_times_mat<T, BT, RT><<<grid, kBlock, smem, ctx->stream>>>(tableOf<T>(A), k, P, j0, bc, al, be, useY, ty, Y->ld);
       LAUNCH_CHECK(ctx);
     }
   }
