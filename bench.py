@@ -396,6 +396,15 @@ def main():
                 "layout_gbs": layout_bytes / (ms_step * 1e-3) / 1e9}
         if split:
             roof["kernel_ms"] = split
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this workload
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tr = json.load(f).get("%s-%d-%s-%d" % (args.workload, args.size, args.layout, b))
+            if tr and world == 1:
+                roof["traffic"] = tr["dram_bytes"]
+                roof["traffic_source"] = "profiles/r01_traffic.json (%s)" % tr["kernel"]
+        except Exception:
+            pass
         out = {
             "metric": "curlcurl_spmv_crs_equiv_gbs", "value": gbs, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",

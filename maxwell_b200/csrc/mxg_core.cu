@@ -1,4 +1,5 @@
 // libmxgpu: context, maps, multivector lifetime and transfers.
+#include <cstdlib>
 #include <cstring>
 
 #include "mxg_internal.h"
@@ -67,6 +68,7 @@ int mxg_ctx_create(int device, mxg_ctx** out) {
   MXG_CUDA(cudaSetDevice(device));
   mxg_ctx* ctx = new mxg_ctx;
   ctx->device = device;
+  ctx->graphsOff = std::getenv("MXG_NO_GRAPH") != nullptr;   // eager enqueues instead of graph replay
   MXG_CUDA(cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device));
   MXG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   MXG_CUDA(cudaStreamCreateWithFlags(&ctx->commStream, cudaStreamNonBlocking));

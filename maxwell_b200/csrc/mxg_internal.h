@@ -100,6 +100,7 @@ struct mxg_ctx {
   double* hPinned = nullptr;           // pinned host staging for small results and dense B
   size_t pinnedBytes = 0;
   int64_t launches = 0;
+  bool graphsOff = false;              // set when stream capture of the halo apply is unavailable
 };
 
 struct mxg_map {
@@ -167,6 +168,17 @@ struct mxg_crs {
   // 1 / diagonal (0 where the diagonal is 0 or absent); only for square operators whose row
   // and domain maps coincide -- the smoothers of the multigrid cycle use it
   void* dInvDiag = nullptr;
+  // most frequent row patterns, passed to the dictionary kernel in its parameter block (host copy)
+  void* hHot = nullptr;
+  int64_t hotRowsCovered = 0;
+  // captured CUDA graphs of the multi-rank apply (pack -> NCCL exchange || interior rows -> boundary rows),
+  // keyed by the operand pointers; replaying one costs a single launch instead of ~10 enqueues
+  struct GraphEntry {
+    uint64_t key;
+    cudaGraphExec_t exec;
+    int launches;
+  };
+  mutable std::vector<GraphEntry> graphs;
 };
 
 namespace mxg {

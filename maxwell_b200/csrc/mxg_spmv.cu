@@ -48,6 +48,18 @@ struct __align__(8) PatEntry<zd> {
 
 using Peer = mxg::HaloPeer;
 
+// The most frequent row patterns travel in the kernel parameter block (constant bank): their
+// entries are fetched with LDC instead of L1 loads. ncu showed the dictionary kernel bound by L1
+// data-pipe wavefronts, half of them pattern-table loads; the constant path takes those off L1.
+constexpr int kHotPats = 96;
+template <class T>
+struct HotTable {
+  static constexpr int kEntries = sizeof(T) == 8 ? 960 : 600;
+  PatEntry<T> e[kEntries];
+  uint16_t off[kHotPats + 1];
+  int nHot;
+};
+
 // ---- exact (unfused) accumulation --------------------------------------------------------
 __device__ __forceinline__ void accum(double& acc, double v, double x) { acc = __dadd_rn(acc, __dmul_rn(v, x)); }
 __device__ __forceinline__ void accum(zd& acc, zd v, zd x) {
@@ -96,12 +108,16 @@ constexpr int kUnroll = 4;
 template <class T, bool GHOST, int NV>
 __global__ void __launch_bounds__(kBlock) k_spmm_dict(int64_t rowBegin, int64_t rowEnd, const int32_t* __restrict__ rowPat,
                                                       const int32_t* __restrict__ patOff, const PatEntry<T>* __restrict__ pat,
+                                                      const __grid_constant__ HotTable<T> H,
                                                       XSource<T> X, ColTable<T> Y, int nvec, Epilogue<T> ep) {
   const int64_t row = rowBegin + blockIdx.x * int64_t(kBlock) + threadIdx.x;
   if (row >= rowEnd) return;
   const int32_t p = rowPat[row];
   if (p < 0) return;
-  const int32_t o = __ldg(patOff + p), oe = __ldg(patOff + p + 1);
+  const bool hot = p < H.nHot;   // pattern entries come from the constant bank (LDC) instead of L1
+  int32_t o, oe;
+  if (hot) { o = H.off[p]; oe = H.off[p + 1]; }
+  else { o = __ldg(patOff + p); oe = __ldg(patOff + p + 1); }
   for (int j0 = 0; j0 < nvec; j0 += NV) {
     T acc[NV];
 #pragma unroll
@@ -110,7 +126,8 @@ __global__ void __launch_bounds__(kBlock) k_spmm_dict(int64_t rowBegin, int64_t 
     // (ncu: l1tex__data_pipe_lsu_wavefronts 93%), so every extra load costs time
     int32_t q = o;
     for (; q + 1 < oe; q += 2) {
-      const PatEntry<T> e0 = pat[q], e1 = pat[q + 1];
+      const PatEntry<T> e0 = hot ? H.e[q] : pat[q];
+      const PatEntry<T> e1 = hot ? H.e[q + 1] : pat[q + 1];
       T x0[NV], x1[NV];
 #pragma unroll
       for (int jj = 0; jj < NV; ++jj) {
@@ -123,7 +140,7 @@ __global__ void __launch_bounds__(kBlock) k_spmm_dict(int64_t rowBegin, int64_t 
       for (int jj = 0; jj < NV; ++jj) accum(acc[jj], entryVal(e1), x1[jj]);
     }
     if (q < oe) {
-      const PatEntry<T> e0 = pat[q];
+      const PatEntry<T> e0 = hot ? H.e[q] : pat[q];
 #pragma unroll
       for (int jj = 0; jj < NV; ++jj) accum(acc[jj], entryVal(e0), loadX<T, GHOST>(X, min(j0 + jj, nvec - 1), row + e0.d));
     }
@@ -199,18 +216,20 @@ __global__ void __launch_bounds__(kBlock) k_pack(ColTable<T> x, const int32_t* _
 
 template <class T, bool GHOST>
 int launchRange(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, int64_t genBegin, int64_t genEnd, const XSource<T>& X,
-                const ColTable<T>& Y, int nvec, const Epilogue<T>& ep) {
+                const ColTable<T>& Y, int nvec, const Epilogue<T>& ep, cudaStream_t st = nullptr) {
   mxg_ctx* ctx = A->ctx;
+  if (!st) st = ctx->stream;
   if (ctx->profiling) MXG_CUDA(cudaEventRecord(ctx->prof[1], ctx->stream));
   if (A->dictRows > 0 && rowEnd > rowBegin) {
     const int64_t blocks = (rowEnd - rowBegin + kBlock - 1) / kBlock;
     auto pat = static_cast<const PatEntry<T>*>(A->dPat);
+    const HotTable<T>& H = *static_cast<const HotTable<T>*>(A->hHot);
     if (nvec == 1)
-      k_spmm_dict<T, GHOST, 1><<<blocks, kBlock, 0, ctx->stream>>>(rowBegin, rowEnd, A->dRowPat, A->dPatOff, pat, X, Y, nvec, ep);
+      k_spmm_dict<T, GHOST, 1><<<blocks, kBlock, 0, st>>>(rowBegin, rowEnd, A->dRowPat, A->dPatOff, pat, H, X, Y, nvec, ep);
     else if (nvec == 2)
-      k_spmm_dict<T, GHOST, 2><<<blocks, kBlock, 0, ctx->stream>>>(rowBegin, rowEnd, A->dRowPat, A->dPatOff, pat, X, Y, nvec, ep);
+      k_spmm_dict<T, GHOST, 2><<<blocks, kBlock, 0, st>>>(rowBegin, rowEnd, A->dRowPat, A->dPatOff, pat, H, X, Y, nvec, ep);
     else
-      k_spmm_dict<T, GHOST, 4><<<blocks, kBlock, 0, ctx->stream>>>(rowBegin, rowEnd, A->dRowPat, A->dPatOff, pat, X, Y, nvec, ep);
+      k_spmm_dict<T, GHOST, 4><<<blocks, kBlock, 0, st>>>(rowBegin, rowEnd, A->dRowPat, A->dPatOff, pat, H, X, Y, nvec, ep);
     LAUNCH_CHECK(ctx);
   }
   if (ctx->profiling) MXG_CUDA(cudaEventRecord(ctx->prof[2], ctx->stream));
@@ -218,43 +237,29 @@ int launchRange(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, int64_t genB
     const int64_t blocks = (genEnd - genBegin + kBlock - 1) / kBlock;
     auto val = static_cast<const T*>(A->dVal);
     if (nvec == 1)
-      k_spmm_sell<T, GHOST, 1><<<blocks, kBlock, 0, ctx->stream>>>(genBegin, genEnd, A->dGenRow, A->dGenLen, A->dSlicePtr, A->dCol, val, X, Y, nvec, ep);
+      k_spmm_sell<T, GHOST, 1><<<blocks, kBlock, 0, st>>>(genBegin, genEnd, A->dGenRow, A->dGenLen, A->dSlicePtr, A->dCol, val, X, Y, nvec, ep);
     else if (nvec == 2)
-      k_spmm_sell<T, GHOST, 2><<<blocks, kBlock, 0, ctx->stream>>>(genBegin, genEnd, A->dGenRow, A->dGenLen, A->dSlicePtr, A->dCol, val, X, Y, nvec, ep);
+      k_spmm_sell<T, GHOST, 2><<<blocks, kBlock, 0, st>>>(genBegin, genEnd, A->dGenRow, A->dGenLen, A->dSlicePtr, A->dCol, val, X, Y, nvec, ep);
     else
-      k_spmm_sell<T, GHOST, 4><<<blocks, kBlock, 0, ctx->stream>>>(genBegin, genEnd, A->dGenRow, A->dGenLen, A->dSlicePtr, A->dCol, val, X, Y, nvec, ep);
+      k_spmm_sell<T, GHOST, 4><<<blocks, kBlock, 0, st>>>(genBegin, genEnd, A->dGenRow, A->dGenLen, A->dSlicePtr, A->dCol, val, X, Y, nvec, ep);
     LAUNCH_CHECK(ctx);
   }
   if (ctx->profiling) MXG_CUDA(cudaEventRecord(ctx->prof[3], ctx->stream));
   return MXG_OK;
 }
 
+inline uint64_t mix64(uint64_t h, uint64_t v) {
+  h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+  h *= 0xBF58476D1CE4E5B9ull;
+  return h ^ (h >> 29);
+}
+
+// pack -> grouped ncclSend/ncclRecv on the communication stream || interior rows -> boundary rows
 template <class T>
-int applyImpl(const mxg_crs* A, const mxg_mv* x, mxg_mv* y, const Epilogue<T>& ep) {
+int haloSequence(const mxg_crs* A, const XSource<T>& X, const ColTable<T>& Y, int nvec, const Epilogue<T>& ep) {
   mxg_ctx* ctx = A->ctx;
-  const int nvec = x->ncols;
   constexpr int w = sizeof(T) / sizeof(double);
   const int64_t gTot = A->gLo + A->gHi;
-  const bool halo = ctx->nranks > 1 && (gTot > 0 || A->sendTotal > 0);
-  if (halo && A->haloCols < nvec) {
-    MXG_CUDA(cudaStreamSynchronize(ctx->stream));
-    MXG_CUDA(cudaStreamSynchronize(ctx->commStream));
-    if (A->dSendBuf) MXG_CUDA(cudaFree(A->dSendBuf));
-    if (A->dGhost) MXG_CUDA(cudaFree(A->dGhost));
-    A->dSendBuf = A->dGhost = nullptr;
-    MXG_CUDA(cudaMalloc(&A->dSendBuf, std::max<size_t>(16, sizeof(T) * A->sendTotal * nvec)));
-    MXG_CUDA(cudaMalloc(&A->dGhost, std::max<size_t>(16, sizeof(T) * gTot * nvec)));
-    A->haloCols = nvec;
-  }
-  XSource<T> X;
-  X.x = tableOf<T>(x);
-  X.ghost = static_cast<const T*>(A->dGhost);
-  X.nLoc = A->nLoc;
-  X.gLo = A->gLo;
-  X.gTot = gTot;
-  ColTable<T> Y = tableOf<T>(y);
-  if (!halo) return launchRange<T, false>(A, 0, A->nRows, 0, A->nGen, X, Y, nvec, ep);
-
   // 1. pack boundary values and start the exchange on the communication stream
   T* sendBuf = static_cast<T*>(A->dSendBuf);
   T* ghost = static_cast<T*>(A->dGhost);
@@ -273,29 +278,90 @@ int applyImpl(const mxg_crs* A, const mxg_mv* x, mxg_mv* y, const Epilogue<T>& e
         MXG_NCCL(ncclRecv(ghost + j * gTot + p.recvStart, size_t(p.recvCount) * w, ncclDouble, p.rank, ctx->comm, ctx->commStream));
     }
   MXG_NCCL(ncclGroupEnd());
-  MXG_CUDA(cudaEventRecord(ctx->evB, ctx->commStream));
-  // 2. rows that need no ghost values overlap with the exchange
-  int rc = launchRange<T, false>(A, A->intBegin, A->intEnd, A->genIntBegin, A->genIntEnd, X, Y, nvec, ep);
-  if (rc) return rc;
-  // 3. boundary rows once the ghost planes have landed
-  MXG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evB, 0));
+  // 2. boundary rows follow the receive ON THE COMMUNICATION STREAM, so exchange + boundary work
+  //    overlap with the interior rows running on the compute stream (they write disjoint rows of y)
+  int rc = MXG_OK;
   if (A->intBegin > 0 || A->genIntBegin > 0) {
-    rc = launchRange<T, true>(A, 0, A->intBegin, 0, A->genIntBegin, X, Y, nvec, ep);
+    rc = launchRange<T, true>(A, 0, A->intBegin, 0, A->genIntBegin, X, Y, nvec, ep, ctx->commStream);
     if (rc) return rc;
   }
   if (A->intEnd < A->nRows || A->genIntEnd < A->nGen) {
-    rc = launchRange<T, true>(A, A->intEnd, A->nRows, A->genIntEnd, A->nGen, X, Y, nvec, ep);
+    rc = launchRange<T, true>(A, A->intEnd, A->nRows, A->genIntEnd, A->nGen, X, Y, nvec, ep, ctx->commStream);
     if (rc) return rc;
   }
+  MXG_CUDA(cudaEventRecord(ctx->evB, ctx->commStream));
+  // 3. rows that need no ghost values
+  rc = launchRange<T, false>(A, A->intBegin, A->intEnd, A->genIntBegin, A->genIntEnd, X, Y, nvec, ep);
+  if (rc) return rc;
+  MXG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->evB, 0));
   return MXG_OK;
 }
 
-// ---- host-side layout construction --------------------------------------------------------
-inline uint64_t mix64(uint64_t h, uint64_t v) {
-  h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
-  h *= 0xBF58476D1CE4E5B9ull;
-  return h ^ (h >> 29);
+template <class T>
+int applyImpl(const mxg_crs* A, const mxg_mv* x, mxg_mv* y, const Epilogue<T>& ep) {
+  mxg_ctx* ctx = A->ctx;
+  const int nvec = x->ncols;
+  constexpr int w = sizeof(T) / sizeof(double);
+  const int64_t gTot = A->gLo + A->gHi;
+  const bool halo = ctx->nranks > 1 && (gTot > 0 || A->sendTotal > 0);
+  if (halo && A->haloCols < nvec) {
+    MXG_CUDA(cudaStreamSynchronize(ctx->stream));
+    MXG_CUDA(cudaStreamSynchronize(ctx->commStream));
+    if (A->dSendBuf) MXG_CUDA(cudaFree(A->dSendBuf));
+    if (A->dGhost) MXG_CUDA(cudaFree(A->dGhost));
+    A->dSendBuf = A->dGhost = nullptr;
+    for (auto& g : A->graphs) cudaGraphExecDestroy(g.exec);
+    A->graphs.clear();
+    MXG_CUDA(cudaMalloc(&A->dSendBuf, std::max<size_t>(16, sizeof(T) * A->sendTotal * nvec)));
+    MXG_CUDA(cudaMalloc(&A->dGhost, std::max<size_t>(16, sizeof(T) * gTot * nvec)));
+    A->haloCols = nvec;
+  }
+  XSource<T> X;
+  X.x = tableOf<T>(x);
+  X.ghost = static_cast<const T*>(A->dGhost);
+  X.nLoc = A->nLoc;
+  X.gLo = A->gLo;
+  X.gTot = gTot;
+  ColTable<T> Y = tableOf<T>(y);
+  if (!halo) return launchRange<T, false>(A, 0, A->nRows, 0, A->nGen, X, Y, nvec, ep);
+
+  // The multi-rank apply is ~10 enqueues (pack, events, NCCL group, 2-6 kernels) for tens of
+  // microseconds of GPU work, i.e. launch-bound. Capture it once per operand set and replay.
+  if (!ctx->graphsOff && !ctx->profiling) {
+    uint64_t key = mix64(0xC0FFEEull, uint64_t(nvec));
+    for (int j = 0; j < nvec; ++j) { key = mix64(key, uint64_t(x->col[j])); key = mix64(key, uint64_t(y->col[j])); }
+    uint64_t epBits[(sizeof(Epilogue<T>) + 7) / 8] = {};
+    std::memcpy(epBits, &ep, sizeof(ep));
+    for (uint64_t b : epBits) key = mix64(key, b);
+    for (const auto& g : A->graphs)
+      if (g.key == key) {
+        MXG_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+        ctx->launches += g.launches;
+        return MXG_OK;
+      }
+    const int64_t before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+      const int rcCap = haloSequence<T>(A, X, Y, nvec, ep);
+      const cudaError_t endErr = cudaStreamEndCapture(ctx->stream, &graph);
+      cudaGraphExec_t exec = nullptr;
+      if (rcCap == MXG_OK && endErr == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+        if (A->graphs.size() >= 32) { cudaGraphExecDestroy(A->graphs.front().exec); A->graphs.erase(A->graphs.begin()); }
+        A->graphs.push_back({key, exec, int(ctx->launches - before)});
+        MXG_CUDA(cudaGraphLaunch(exec, ctx->stream));
+        return MXG_OK;
+      }
+      if (graph) cudaGraphDestroy(graph);
+    }
+    cudaGetLastError();          // clear the capture error and fall back to eager enqueues for good
+    ctx->launches = before;
+    ctx->graphsOff = true;
+  }
+  return haloSequence<T>(A, X, Y, nvec, ep);
 }
+
+// ---- host-side layout construction --------------------------------------------------------
 
 template <class P>
 int uploadVec(const std::vector<P>& v, P** out, size_t* bytes, mxg_ctx* ctx) {
@@ -512,7 +578,11 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
     }
     const int minCount = 4;
     std::vector<int32_t> candToPat(cands.size(), -1);
-    for (size_t c = 0; c < cands.size(); ++c) {
+    // most frequent patterns first: the leading ones ride in the kernel parameter block
+    std::vector<size_t> order(cands.size());
+    for (size_t c = 0; c < cands.size(); ++c) order[c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cands[a].count > cands[b].count; });
+    for (size_t c : order) {
       if (cands[c].count < minCount) continue;
       candToPat[c] = int32_t(patOff.size() - 1);
       const int64_t r = cands[c].row;
@@ -530,6 +600,22 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
   }
   A->numPats = int64_t(patOff.size()) - 1;
   A->patEntries = int64_t(pat.size());
+  {  // hot table: the most frequent patterns, as many as fit
+    auto* H = new HotTable<T>();
+    std::memset(H, 0, sizeof(*H));
+    int nh = 0;
+    while (nh < kHotPats && nh < A->numPats && patOff[nh + 1] <= HotTable<T>::kEntries) ++nh;
+    // Measured on B200 (pillbox-256): 0.351 ms with the constant path vs 0.305 ms without -- a warp
+    // holds ~3 different patterns, and divergent LDC replays cost more than L1 broadcast loads.
+    // The path is therefore opt-in (MXG_SPMV_HOT=1); see profiles/README_r01.md.
+    if (!std::getenv("MXG_SPMV_HOT")) nh = 0;
+    H->nHot = nh;
+    for (int q = 0; q <= nh; ++q) H->off[q] = uint16_t(patOff[q]);
+    for (int q = 0; q < (nh ? patOff[nh] : 0); ++q) H->e[q] = pat[q];
+    A->hHot = H;
+    A->hotRowsCovered = 0;
+    for (int64_t r = 0; r < nRows; ++r) A->hotRowsCovered += (rowPat[r] >= 0 && rowPat[r] < nh);
+  }
 
   // ---- general rows in sliced ELL; the three row classes (leading boundary, interior,
   // trailing boundary) each start on a slice boundary so they can be launched separately
@@ -660,9 +746,11 @@ int mxg_crs_destroy(mxg_crs* A) {
   cudaSetDevice(A->ctx->device);
   cudaStreamSynchronize(A->ctx->stream);
   cudaStreamSynchronize(A->ctx->commStream);
+  for (auto& g : A->graphs) cudaGraphExecDestroy(g.exec);
   void* ptrs[] = {A->dRowPat, A->dPatOff, A->dPat, A->dGenRow, A->dGenLen, A->dSlicePtr, A->dCol, A->dVal, A->dSendIdx, A->dSendBuf, A->dGhost, A->dInvDiag};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (A->hHot) { if (A->isComplex) delete static_cast<HotTable<zd>*>(A->hHot); else delete static_cast<HotTable<double>*>(A->hHot); }
   mxg_map_destroy(A->rowMap);
   mxg_map_destroy(A->domMap);
   delete A;
