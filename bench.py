@@ -321,15 +321,17 @@ def main():
     ms_step = ms / args.steps
 
     # per-kernel split (1 GPU): averaged over a few profiled applies
+    # (several ranks: dict_ms = interior rows incl. the final wait, sell_ms = boundary rows, pre_ms = NCCL exchange)
     split = None
-    if world == 1:
-        acc = {"dict_ms": 0.0, "sell_ms": 0.0, "total_ms": 0.0}
-        reps = 20
-        for _ in range(reps):
-            r = A.apply_timed(x, y)
-            for k in acc:
-                acc[k] += r[k] / reps
-        split = acc
+    acc = {"dict_ms": 0.0, "sell_ms": 0.0, "pre_ms": 0.0, "total_ms": 0.0}
+    reps = 20
+    for _ in range(reps):
+        r = A.apply_timed(x, y)
+        for k in acc:
+            acc[k] += r[k] / reps
+    split = acc
+    if world > 1:
+        split = {"interior_ms": acc["dict_ms"], "boundary_ms": acc["sell_ms"], "nccl_ms": acc["pre_ms"], "total_ms": acc["total_ms"]}
 
     # ---- e2e: host buffers through the C ABI (H2D of x, apply, D2H of y every step) ------------
     n_loc = r1 - r0

@@ -71,9 +71,17 @@ int mxg_ctx_create(int device, mxg_ctx** out) {
   ctx->graphsOff = std::getenv("MXG_NO_GRAPH") != nullptr;   // eager enqueues instead of graph replay
   MXG_CUDA(cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device));
   MXG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  MXG_CUDA(cudaStreamCreateWithFlags(&ctx->commStream, cudaStreamNonBlocking));
+  {
+    // halo exchange + boundary rows get scheduling priority over the bulk interior rows
+    int lo = 0, hi = 0;
+    MXG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    MXG_CUDA(cudaStreamCreateWithPriority(&ctx->commStream, cudaStreamNonBlocking, hi));
+  }
   MXG_CUDA(cudaEventCreateWithFlags(&ctx->evA, cudaEventDisableTiming));
   MXG_CUDA(cudaEventCreateWithFlags(&ctx->evB, cudaEventDisableTiming));
+  MXG_CUDA(cudaHostAlloc(&ctx->hErr, sizeof(int), cudaHostAllocMapped));
+  *ctx->hErr = 0;
+  MXG_CUDA(cudaHostGetDevicePointer(&ctx->dErr, ctx->hErr, 0));
   int rc = ensureScratch(ctx, 1u << 20);
   if (rc) return rc;
   rc = ensurePinned(ctx, 1u << 20);
@@ -90,6 +98,7 @@ int mxg_ctx_destroy(mxg_ctx* ctx) {
   if (ctx->comm) ncclCommDestroy(ctx->comm);
   if (ctx->dScratch) cudaFree(ctx->dScratch);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+  if (ctx->hErr) cudaFreeHost(ctx->hErr);
   cudaEventDestroy(ctx->evA);
   cudaEventDestroy(ctx->evB);
   for (auto& e : ctx->timer)

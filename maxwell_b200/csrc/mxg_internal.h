@@ -91,7 +91,7 @@ struct mxg_ctx {
   cudaStream_t commStream = nullptr;   // halo exchange stream
   cudaEvent_t evA = nullptr, evB = nullptr;
   cudaEvent_t timer[16] = {};          // user timing slots (created lazily)
-  cudaEvent_t prof[6] = {};            // per-kernel profiling events
+  cudaEvent_t prof[10] = {};           // per-kernel profiling events
   bool profiling = false;
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
@@ -101,6 +101,8 @@ struct mxg_ctx {
   size_t pinnedBytes = 0;
   int64_t launches = 0;
   bool graphsOff = false;              // set when stream capture of the halo apply is unavailable
+  int* hErr = nullptr;                 // mapped pinned error word written by device-side waits
+  int* dErr = nullptr;
 };
 
 struct mxg_map {
@@ -179,6 +181,23 @@ struct mxg_crs {
     int launches;
   };
   mutable std::vector<GraphEntry> graphs;
+  // Direct peer-memory halo exchange: boundary values are stored straight into the neighbour's ghost
+  // buffer over NVLink by the pack kernel, followed by an epoch flag; no NCCL call per apply.
+  struct P2P {
+    bool on = false;
+    int capCols = 0;
+    void* ghost = nullptr;                  // [2][capCols][gTot] scalars, IPC-exported (double buffered by epoch parity)
+    unsigned long long* flags = nullptr;    // [nranks] epochs written by the senders, IPC-exported
+    unsigned long long* epoch = nullptr;    // local apply counter
+    unsigned int* done = nullptr;           // block-completion counter of the pack kernel
+    int npeers = 0;
+    int peerRank[8];
+    void* peerGhost[8];
+    unsigned long long* peerFlag[8];
+    int64_t remoteStart[8], remoteGTot[8];
+    std::vector<void*> opened;
+  };
+  mutable P2P p2p;
 };
 
 namespace mxg {
