@@ -421,6 +421,16 @@ inline Csr<double> toKForm(const Csr<cplx>& A) {
 // Simulation container (MxEMSim.cpp:54-225) and named operators (MxEMOps.cpp:39-168,
 // MxMagWaveOp.cpp:137-245).
 // ---------------------------------------------------------------------------------------
+// MxDielectric.{hpp,cpp}: a shape with a (possibly anisotropic, possibly complex) permittivity tensor
+struct Dielectric {
+  std::string name;
+  std::shared_ptr<Shape> shape;
+  cplx eps[3][3];
+  bool isDiag() const {  // MxDielectric.cpp:27-36 (dEps = 0)
+    return !(std::abs(eps[0][1]) > 0 || std::abs(eps[0][2]) > 0 || std::abs(eps[1][2]) > 0);
+  }
+};
+
 struct Sim {
   Grid grid;
   BCType lower[3] = {PERIODIC, PERIODIC, PERIODIC}, upper[3] = {PERIODIC, PERIODIC, PERIODIC};
@@ -428,7 +438,8 @@ struct Sim {
   std::shared_ptr<Shape> pec;
   double dmFrac = 0.0;
   bool literalUpperPeriodicE = false;
-  std::unique_ptr<Field> B, E, Psi;
+  std::unique_ptr<Field> B, E, D, Psi;
+  std::vector<Dielectric> diels;
 
   Sim(I3 n, D3 o, D3 l) : grid(n, o, l) {}
 
@@ -440,20 +451,236 @@ struct Sim {
     E->setBCs(lower, upper);
     Psi.reset(new Field(&grid, FIELD_PSI, B.get()));
     Psi->setBCs(lower, upper);
-    Field* fields[3] = {B.get(), E.get(), Psi.get()};
+    std::vector<Field*> fields = {B.get(), E.get()};
+    if (hasDielectric()) {                      // MxEMSim.cpp:90-95: the D field exists only with dielectrics
+      D.reset(new Field(&grid, FIELD_D));
+      D->setBCs(lower, upper);
+      fields.push_back(D.get());
+    }
+    fields.push_back(Psi.get());
     for (Field* f : fields) {
       f->setPhaseShifts(phaseShifts);
       f->literalUpperPeriodicE = literalUpperPeriodicE;
     }
     if (pec) {
-      for (Field* f : fields) f->addShapeRep(*pec, "pec", true);  // B first, then E, psi
-    } else {
-      for (Field* f : fields) f->setMap();
+      for (Field* f : fields) f->addShapeRep(*pec, "pec", true);  // B first, then E, [D], psi
     }
+    // MxEMSim.cpp:134-148: dielectric fractions on every field except B (and H); no region
+    for (Field* f : fields)
+      if (f->kind != FIELD_B)
+        for (const Dielectric& d : diels) f->addShapeRep(*d.shape, d.name, false);
+    if (!pec)
+      for (Field* f : fields)
+        if (f->kind != FIELD_D) f->setMap();
+    if (D) D->shareMap(*E);                      // MxEMSim.cpp:186-190
   }
+  bool hasDielectric() const { return !diels.empty(); }
   bool hasPEC() const { return bool(pec); }
   bool isComplex() const { return phaseShifts[0] != 0 || phaseShifts[1] != 0 || phaseShifts[2] != 0; }
 };
+
+// ---- MxYeeFitInvEps (second-order anisotropic inverse permittivity) ---------------------------
+struct M3 {
+  cplx a[3][3];
+};
+inline M3 m3Zero() { M3 m; for (auto& r : m.a) for (auto& v : r) v = 0.0; return m; }
+inline M3 m3Eye() { M3 m = m3Zero(); for (int i = 0; i < 3; ++i) m.a[i][i] = 1.0; return m; }
+inline M3 m3Mul(const M3& x, const M3& y) {
+  M3 r = m3Zero();
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      cplx s = 0.0;
+      for (int k = 0; k < 3; ++k) s += x.a[i][k] * y.a[k][j];
+      r.a[i][j] = s;
+    }
+  return r;
+}
+inline M3 m3Inv(const M3& m) {
+  const cplx (*a)[3] = m.a;
+  const cplx det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+                   a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+  M3 r;
+  r.a[0][0] = (a[1][1] * a[2][2] - a[1][2] * a[2][1]) / det;
+  r.a[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) / det;
+  r.a[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) / det;
+  r.a[1][0] = (a[1][2] * a[2][0] - a[1][0] * a[2][2]) / det;
+  r.a[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) / det;
+  r.a[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) / det;
+  r.a[2][0] = (a[1][0] * a[2][1] - a[1][1] * a[2][0]) / det;
+  r.a[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) / det;
+  r.a[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) / det;
+  return r;
+}
+
+struct EpsStencil {
+  int comps[9];
+  I3 cells[9];
+};
+// MxYeeFitInvEps.cpp:33-72: E_c0(cell) couples to D_c0(cell), four D_c1 and four D_c2 neighbours
+inline EpsStencil epsStencil(int c0, const I3& cell) {
+  const int c1 = (c0 + 1) % 3, c2 = (c1 + 1) % 3;
+  EpsStencil st;
+  st.comps[0] = c0;
+  for (int i = 1; i < 5; ++i) st.comps[i] = c1;
+  for (int i = 5; i < 9; ++i) st.comps[i] = c2;
+  for (int i = 0; i < 9; ++i) st.cells[i] = cell;
+  st.cells[1][c1]--;
+  st.cells[3][c0]++; st.cells[3][c1]--;
+  st.cells[4][c0]++;
+  st.cells[5][c2]--;
+  st.cells[7][c0]++; st.cells[7][c2]--;
+  st.cells[8][c0]++;
+  return st;
+}
+
+// gamma / pi averaging of one (E_c0, D_c1, D_c2) triplet (MxYeeFitInvEps.cpp:327-416)
+inline M3 tupleUpdate(const Sim& s, const int comps[3], const I3 cells[3], const D3& n) {
+  const Field &E = *s.E, &D = *s.D;
+  const cplx nc[3] = {n[0], n[1], n[2]};
+  M3 aveGamma = m3Zero(), avePi = m3Zero();
+  double lsum[3] = {0, 0, 0}, asum[3] = {0, 0, 0};
+  auto accumulate = [&](const cplx eps[3][3], const double lfr[3], const double afr[3]) {
+    M3 e, nn, eyeMinusEps;
+    for (int j = 0; j < 3; ++j)
+      for (int k = 0; k < 3; ++k) {
+        e.a[j][k] = eps[j][k];
+        nn.a[j][k] = nc[j] * nc[k];
+        eyeMinusEps.a[j][k] = (j == k ? cplx(1.0) : cplx(0.0)) - eps[j][k];
+      }
+    cplx nEn = 0.0;
+    for (int j = 0; j < 3; ++j) {
+      cplx t = 0.0;
+      for (int k = 0; k < 3; ++k) t += e.a[j][k] * nc[k];
+      nEn += nc[j] * t;
+    }
+    M3 gamma = m3Mul(nn, eyeMinusEps);
+    for (int j = 0; j < 3; ++j)
+      for (int k = 0; k < 3; ++k) gamma.a[j][k] = (j == k ? cplx(1.0) : cplx(0.0)) + gamma.a[j][k] / nEn;
+    const M3 pi = m3Mul(e, gamma);
+    for (int j = 0; j < 3; ++j)      // cartProjs[j] * frac[j] selects row j
+      for (int k = 0; k < 3; ++k) {
+        aveGamma.a[j][k] += lfr[j] * gamma.a[j][k];
+        avePi.a[j][k] += afr[j] * pi.a[j][k];
+      }
+  };
+  for (const Dielectric& d : s.diels) {
+    double lfr[3], afr[3];
+    for (int j = 0; j < 3; ++j) {
+      const int c = comps[j];
+      lfr[c] = E.frac(c, cells[j], d.name);
+      afr[c] = D.frac(c, cells[j], d.name);
+      lsum[c] += lfr[c];
+      asum[c] += afr[c];
+    }
+    accumulate(d.eps, lfr, afr);
+  }
+  cplx bg[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};    // background dielectric: vacuum
+  double lfr[3], afr[3];
+  for (int j = 0; j < 3; ++j) { lfr[j] = 1.0 - lsum[j]; afr[j] = 1.0 - asum[j]; }
+  accumulate(bg, lfr, afr);
+  return m3Mul(aveGamma, m3Inv(avePi));
+}
+
+// MxYeeFitInvEps.cpp:420-596 (no PML). Entries whose D column is not in the map are dropped (the
+// reference would hand Epetra a column outside the domain map); explicit zeros in the map are kept.
+template <class S>
+Csr<S> invEps(const Sim& s) {
+  const Field &E = *s.E, &D = *s.D;
+  Csr<S> m;
+  startMatrix(m, E, D);
+  RowBuf<S> row;
+  for (size_t r = 0; r < E.gids.size(); ++r) {
+    I3 cell; int c0;
+    cellCompOf(E, E.gids[r], cell, c0);
+    bool inDiel = false, epsIsDiag = false;
+    const Dielectric* diel = nullptr;
+    for (const Dielectric& d : s.diels) {
+      const double l0 = E.frac(c0, cell, d.name), a0 = D.frac(c0, cell, d.name);
+      if (l0 == 1 && a0 == 1) { inDiel = true; epsIsDiag = d.isDiag(); diel = &d; break; }
+      else if (l0 == 0 && a0 == 0) continue;
+      else { inDiel = true; diel = &d; break; }
+    }
+    if (!inDiel) epsIsDiag = true;   // background (vacuum) is diagonal
+    if (epsIsDiag) {
+      const cplx e00 = inDiel ? diel->eps[c0][c0] : cplx(1.0);
+      const cplx v = D.factor(c0, cell) / e00;
+      row.add(int32_t(r), fromFactor<S>(v));
+    } else {
+      const EpsStencil st = epsStencil(c0, cell);
+      // interface normal (MxYeeFitInvEps.cpp:271-324)
+      D3 nsum{0, 0, 0};
+      std::vector<D3> norms;
+      for (const Dielectric& d : s.diels) {
+        bool cut = false;
+        for (int j = 0; j < 9; ++j) {
+          const double lf = E.frac(st.comps[j], st.cells[j], d.name), af = D.frac(st.comps[j], st.cells[j], d.name);
+          if ((lf != 0 && lf != 1) || (af != 0 && af != 1)) cut = true;
+        }
+        if (cut) {
+          const D3 g = d.shape->grad(E.g->nodeCoord(st.cells[0]) + E.xi[st.comps[0]]);
+          norms.push_back(g / norm(g));
+        }
+      }
+      D3 n{1, 0, 0};
+      if (!norms.empty()) {
+        for (size_t i = 0; i < norms.size(); ++i) {
+          const double sg = (i > 0 && dot(norms[0], norms[i]) < 0) ? -1.0 : 1.0;
+          nsum = nsum + sg * norms[i];
+        }
+        n = nsum / norm(nsum);
+      }
+      // triplets (MxYeeFitInvEps.cpp:126-171)
+      static const int T[8][3] = {{0, 1, 5}, {0, 1, 6}, {0, 2, 5}, {0, 2, 6}, {0, 3, 7}, {0, 3, 8}, {0, 4, 7}, {0, 4, 8}};
+      std::vector<int> used;
+      for (int t = 0; t < 8; ++t) {
+        bool use = true;
+        if (s.hasPEC())
+          for (int j = 0; j < 3; ++j)
+            if (E.frac(st.comps[T[t][j]], st.cells[T[t][j]], "pec") == 0) use = false;
+        if (use) used.push_back(t);
+      }
+      cplx vals[9];
+      for (auto& v : vals) v = 0.0;
+      for (int t : used) {
+        int comps[3]; I3 cells[3];
+        for (int j = 0; j < 3; ++j) { comps[j] = st.comps[T[t][j]]; cells[j] = st.cells[T[t][j]]; }
+        const M3 ie = tupleUpdate(s, comps, cells, n);
+        for (int j = 0; j < 3; ++j) vals[T[t][j]] += ie.a[c0][comps[j]] / double(used.size());
+      }
+      for (int i = 0; i < 9; ++i) {
+        const cplx v = vals[i] * D.factor(st.comps[i], st.cells[i]);
+        const int32_t l = D.lid(D.gid(st.comps[i], st.cells[i]));
+        if (l >= 0) row.add(l, fromFactor<S>(v));
+      }
+    }
+    row.flushInto(m);
+  }
+  return m;
+}
+
+// MxYeeFitInvEps.cpp:650-725: cell-averaged scalar 1/eps on the psi field (3 / trace(eps))
+template <class S>
+Csr<S> invEpsVolAve(const Sim& s) {
+  const Field& Psi = *s.Psi;
+  Csr<S> m;
+  startMatrix(m, Psi, Psi);
+  for (size_t i = 0; i < Psi.gids.size(); ++i) {
+    I3 cell; int c;
+    cellCompOf(Psi, Psi.gids[i], cell, c);
+    double sum = 0;
+    cplx ave = 0.0;
+    for (const Dielectric& d : s.diels) {
+      const double f = Psi.frac(c, cell, d.name);
+      sum += f;
+      ave += f * (3.0 / (d.eps[0][0] + d.eps[1][1] + d.eps[2][2]));
+    }
+    ave += (1.0 - sum) * cplx(1.0);
+    m.col.push_back(int32_t(i));
+    m.val.push_back(fromFactor<S>(ave));
+    m.rowptr.push_back(int64_t(i + 1));
+  }
+  return m;
+}
 
 template <class S>
 Csr<S> buildOp(const Sim& s, const std::string& name) {
@@ -465,14 +692,18 @@ Csr<S> buildOp(const Sim& s, const std::string& name) {
   if (name == "dmA") return fracs<S>(B, false, 0.e-12);        // MxEMOps.cpp:56-58
   if (name == "dmL") return fracs<S>(E, false, 0.e-6);         // MxEMOps.cpp:61-63
   if (name == "dmVInv") return fracs<S>(Psi, true, 0.e-6);     // MxEMOps.cpp:125-127
+  if (name == "invEps") return invEps<S>(s);                    // MxEMOps.cpp:72-81
+  if (name == "invEpsVolAve") return invEpsVolAve<S>(s);
   if (name == "curlCurl") {                                     // MxMagWaveOp.cpp:144-153
     Csr<S> m = curlB<S>(B, E);
+    if (s.hasDielectric()) m = multiply(invEps<S>(s), m);
     if (s.hasPEC()) m = multiply(fracs<S>(E, false, 0.e-6), m);
     return multiply(curlE<S>(B, E), m);
   }
   if (name == "gradDiv") {                                      // MxMagWaveOp.cpp:156-179
     Csr<S> m = s.hasPEC() ? multiply(divB<S>(B, Psi), fracs<S>(B, false, 0.e-12)) : divB<S>(B, Psi);
     if (s.hasPEC()) m = multiply(fracs<S>(Psi, true, 0.e-6), m);
+    if (s.hasDielectric()) m = multiply(invEpsVolAve<S>(s), m);
     m = multiply(gradPsi<S>(B, Psi), m);
     if (s.hasPEC()) m = multiply(fracs<S>(B, false, 0.e-12), m);
     return m;

@@ -68,6 +68,15 @@ void mxo_sim_set_phase_shifts(void* s, const double ph[3]) {
   for (int i = 0; i < 3; ++i) sim->phaseShifts[i] = ph[i];
 }
 void mxo_sim_set_pec(void* s, void* shape) { static_cast<Sim*>(s)->pec = *static_cast<std::shared_ptr<Shape>*>(shape); }
+// eps: 9 complex entries (18 doubles), row-major
+void mxo_sim_add_dielectric(void* s, void* shape, const double* eps, const char* name) {
+  Dielectric d;
+  d.name = name;
+  d.shape = *static_cast<std::shared_ptr<Shape>*>(shape);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) d.eps[i][j] = cplx(eps[2 * (3 * i + j)], eps[2 * (3 * i + j) + 1]);
+  static_cast<Sim*>(s)->diels.push_back(d);
+}
 void mxo_sim_set_literal_upper_periodic_e(void* s, int on) { static_cast<Sim*>(s)->literalUpperPeriodicE = on != 0; }
 int mxo_sim_setup(void* s) { return guard([&] { static_cast<Sim*>(s)->setup(); }); }
 
@@ -75,6 +84,7 @@ static const Field* fieldOf(const Sim* sim, const char* name) {
   const std::string n(name);
   if (n == "bfield") return sim->B.get();
   if (n == "efield") return sim->E.get();
+  if (n == "dfield" && sim->D) return sim->D.get();
   if (n == "psifield") return sim->Psi.get();
   throw std::runtime_error("mxo: unknown field '" + n + "'");
 }

@@ -45,6 +45,7 @@ def lib():
             "mxo_sim_set_bcs": (None, [vp, i3, i3]),
             "mxo_sim_set_phase_shifts": (None, [vp, d3]),
             "mxo_sim_set_pec": (None, [vp, vp]),
+            "mxo_sim_add_dielectric": (None, [vp, vp, vp, cp]),
             "mxo_sim_set_literal_upper_periodic_e": (None, [vp, C.c_int]),
             "mxo_sim_setup": (C.c_int, [vp]),
             "mxo_sim_map_size": (i64, [vp, cp]),
@@ -207,7 +208,7 @@ class Sim:
     """Mirror of MxEMSim (MxEMSim.cpp:54-225) restricted to 3-D, PEC shapes and BCs."""
 
     def __init__(self, n, origin=(0.0, 0.0, 0.0), size=(1.0, 1.0, 1.0), lower=None, upper=None,
-                 phase_shifts=None, pec=None, literal_upper_periodic_e=False):
+                 phase_shifts=None, pec=None, literal_upper_periodic_e=False, dielectrics=()):
         if np.isscalar(n):
             n = (n, n, n)
         L = lib()
@@ -222,6 +223,10 @@ class Sim:
         if pec is not None:
             L.mxo_sim_set_pec(self.h, pec.h)
         L.mxo_sim_set_literal_upper_periodic_e(self.h, int(literal_upper_periodic_e))
+        self._diels = list(dielectrics)
+        for i, (shape, eps) in enumerate(self._diels):
+            e = np.ascontiguousarray(np.asarray(eps, dtype=np.complex128).reshape(3, 3))
+            L.mxo_sim_add_dielectric(self.h, shape.h, e.ctypes.data, ("diel%d" % i).encode())
         _check(L.mxo_sim_setup(self.h))
 
     def map(self, field):
@@ -286,6 +291,27 @@ def pillbox(n, radius=0.4, length=0.8, origin=-0.5, size=1.0):
     caps = Shape.slab(length, (0, 0, 1), (0, 0, 0))
     cav = Shape.intersection([cyl, caps])
     return Sim(n, origin=(origin,) * 3, size=(size,) * 3, pec=cav)
+
+
+def dsphmsph(n, eps=10.0, a=0.37, b=0.49, size=1.0, origin=-0.5):
+    """example/dsphmsph.py: dielectric sphere (radius a, permittivity eps) inside a PEC sphere (radius b).
+    The example runs one octant with PEC/PMC symmetry planes; this helper takes the full ball in a box."""
+    diel = Shape.sphere(a, (0, 0, 0))
+    metal = Shape.sphere(b, (0, 0, 0))
+    e = np.eye(3) * eps if np.isscalar(eps) else np.asarray(eps)
+    return Sim(n, origin=(origin,) * 3, size=(size,) * 3, pec=metal, dielectrics=[(diel, e)])
+
+
+# eps diag [10.225, 10.225, 9.95], off-diag [yz, xz, xy] = [0.6736.., -0.6736.., -0.825] (MxProblem.cpp:501-506)
+_S = 0.67360967926537398
+SAPPHIRE = np.array([[10.225, -0.825, -_S], [-0.825, 10.225, _S], [-_S, _S, 9.95]])
+
+
+def phc_sapphire(n, phase_shifts=(0.0, 0.0, 0.0), r=0.37, eps=None):
+    """example/phc-sapph-r0.37.py:12-22: sapphire sphere in a periodic unit cell, Bloch phase shifts."""
+    sph = Shape.sphere(r, (0, 0, 0))
+    return Sim(n, origin=(-0.5,) * 3, size=(1.0,) * 3, phase_shifts=phase_shifts,
+               dielectrics=[(sph, SAPPHIRE if eps is None else eps)])
 
 
 def vacuum(n, phase_shifts=None, literal=False):
