@@ -497,3 +497,104 @@ class MxSolver {
   const mx::Operator<S>* T_;
   MxSolverParams p_;
 };
+
+// ---- MxMagWaveOp (src/MxMagWaveOp.{h,cpp}): the shift-invert operator the reference hands to Anasazi ------
+//   Apply:  y = P (L - sigma M)^-1 M x            (MxMagWaveOp.cpp:825-943)
+//   with L = vecLapl, M = mRhs (diagonal), and the divergence-cleaning projection
+//   P b = b + gradPsi * scaLapl^-1 * divB * M * b  (:893-924), scaLapl = -(divB M gradPsi) (:208-223).
+// The reference solves both systems with AztecOO GMRES/CG + ML or ILUT (:285-537). Here both are block
+// preconditioned CG on the GPU (valid for sigma below the lowest eigenvalue -- the reference's default
+// automatic shift 0.05 (2 pi / L)^2, src/mx.py:711-712 -- where L - sigma M is positive definite), with the
+// multigrid V-cycle as the vector preconditioner and Jacobi (or a second V-cycle) for the scalar solve.
+struct MxMagWaveOpParams {
+  double shift = 0.0;          // sigma
+  double linTol = 1e-10;       // "linear solver : tol" on |r| / |b|
+  int maxLinIters = 1000;
+  bool hasCurlNull = true;     // 3-D: project out the gradient fields
+};
+
+class MxMagWaveOp : public mx::Operator<double> {
+  typedef MxAnasaziMV<double> MV;
+
+ public:
+  MxMagWaveOp(mxg_crs* vecLapl, mxg_mv* mDiag, mxg_crs* divB, mxg_crs* gradPsi, mxg_crs* scaLapl,
+              const mx::Operator<double>* vecPrec, const mx::Operator<double>* scaPrec, MxMagWaveOpParams p)
+      : L_(vecLapl), m_(mDiag), D_(divB), G_(gradPsi), S_(scaLapl), Tv_(vecPrec), Ts_(scaPrec), p_(p) {}
+
+  // counters the reference prints from its destructor (MxMagWaveOp.cpp:96-115)
+  mutable long numApplies = 0, numVecLinIters = 0, numScaLinIters = 0;
+
+  void Apply(const mx::MultiVec<double>& x, mx::MultiVec<double>& y) const override {
+    const MV& x2 = dynamic_cast<const MV&>(x);
+    MV& y2 = dynamic_cast<MV&>(y);
+    ++numApplies;
+    const int nb = x2.GetNumberVecs();
+    std::shared_ptr<MxMap> bmap = x2.getMap();
+    MV rhs(bmap, nb), bWork(bmap, nb);
+    mx::check(mxg_mv_diag_mult(rhs.getRawMV(), m_, x2.getRawMV()));                       // y = mRhs x (:865)
+    numVecLinIters += pcg([&](const MV& in, MV& out) { applyShifted(in, out); }, Tv_, nullptr, rhs, bWork);   // (:869-885)
+    if (!p_.hasCurlNull) { y2 = bWork; return; }
+    mx::check(mxg_mv_diag_mult(rhs.getRawMV(), m_, bWork.getRawMV()));                    // y = mRhs bWork (:895)
+    std::shared_ptr<MxMap> pmap(new MxMap(mxg_crs_row_map(D_), bmap->getComm(), false));
+    MV psi1(pmap, nb), psi2(pmap, nb);
+    mx::check(mxg_crs_apply(D_, rhs.getRawMV(), psi1.getRawMV()));                         // psi1 = divB y (:896)
+    numScaLinIters += pcg([&](const MV& in, MV& out) { mx::check(mxg_crs_apply(S_, in.getRawMV(), out.getRawMV())); },
+                          Ts_, S_, psi1, psi2);                                             // (:903-913)
+    mx::check(mxg_crs_apply(G_, psi2.getRawMV(), y2.getRawMV()));                          // y = gradPsi psi2 (:919)
+    y2.MvAddMv(1.0, y2, 1.0, bWork);                                                        // y += bWork (:921)
+  }
+
+ private:
+  void applyShifted(const MV& in, MV& out) const {   // out = (L - sigma M) in
+    mx::check(mxg_crs_apply(L_, in.getRawMV(), out.getRawMV()));
+    if (p_.shift != 0.0) {
+      MV t(in.getMap(), in.GetNumberVecs());
+      mx::check(mxg_mv_diag_mult(t.getRawMV(), m_, in.getRawMV()));
+      out.MvAddMv(1.0, out, -p_.shift, t);
+    }
+  }
+  // block preconditioned CG, one independent recurrence per column; returns the iteration count.
+  // prec == nullptr and jac != nullptr: Jacobi with the operator's diagonal; both null: unpreconditioned.
+  template <class ApplyA>
+  long pcg(ApplyA&& A, const mx::Operator<double>* prec, mxg_crs* jac, const MV& b, MV& x) const {
+    const int nb = b.GetNumberVecs();
+    std::shared_ptr<MxMap> map = b.getMap();
+    MV r(b), z(map, nb), pdir(map, nb), q(map, nb), tmp(map, nb);
+    x.MvInit(0.0);
+    std::vector<double> bn, rn, rz(nb), rzNew(nb), pq(nb), alpha(nb), beta(nb);
+    b.MvNorm(bn);
+    auto precond = [&](const MV& in, MV& out) {
+      if (prec) prec->Apply(in, out);
+      else if (jac) mx::check(mxg_crs_jacobi(jac, in.getRawMV(), out.getRawMV()));
+      else out = in;
+    };
+    precond(r, z);
+    pdir = z;
+    r.MvDot(z, rz);
+    long it = 0;
+    for (; it < p_.maxLinIters; ++it) {
+      r.MvNorm(rn);
+      bool done = true;
+      for (int j = 0; j < nb; ++j) done = done && (bn[j] == 0.0 || rn[j] <= p_.linTol * bn[j]);
+      if (done) break;
+      A(pdir, q);
+      pdir.MvDot(q, pq);
+      for (int j = 0; j < nb; ++j) alpha[j] = pq[j] != 0.0 ? rz[j] / pq[j] : 0.0;
+      tmp = pdir; tmp.MvScale(alpha); x.MvAddMv(1.0, x, 1.0, tmp);
+      tmp = q; tmp.MvScale(alpha); r.MvAddMv(1.0, r, -1.0, tmp);
+      precond(r, z);
+      r.MvDot(z, rzNew);
+      for (int j = 0; j < nb; ++j) { beta[j] = rz[j] != 0.0 ? rzNew[j] / rz[j] : 0.0; rz[j] = rzNew[j]; }
+      pdir.MvScale(beta);
+      pdir.MvAddMv(1.0, pdir, 1.0, z);
+    }
+    return it;
+  }
+
+  mxg_crs* L_;
+  mxg_mv* m_;
+  mxg_crs *D_, *G_, *S_;
+  const mx::Operator<double>* Tv_;
+  const mx::Operator<double>* Ts_;
+  MxMagWaveOpParams p_;
+};

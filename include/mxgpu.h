@@ -168,6 +168,9 @@ int mxg_crs_stats(const mxg_crs* A, int64_t out[8]);
  * (MxMagWaveOp.cpp:227-241, applied at :865,895,1132) without a CRS round trip */
 int mxg_mv_diag_mult(mxg_mv* y, const mxg_mv* d, const mxg_mv* x);
 
+/* y = diag(A)^-1 x (Jacobi preconditioner of the projection solve; A must be square on one map) */
+int mxg_crs_jacobi(const mxg_crs* A, const mxg_mv* x, mxg_mv* y);
+
 /* ---- geometric multigrid preconditioner (MxGeoMultigridPrec.{h,cpp}; dead code in the
  * reference, so this follows its structure: setup :98-240, vCycle :243-398, fullVCycle
  * :547-616, ApplyInverse :496-542). Levels are ordered fine -> coarse. ops[l] must be square

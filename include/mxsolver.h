@@ -34,6 +34,13 @@ int mxs_lobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, mxg_mv* 
  * res[j] = |A x_j - theta_j M x_j|_2 / |theta_j| ; div[j] = |D M x_j|_2 / |M x_j|_2 (D may be NULL) */
 int mxs_check_eigensolution(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_crs* divB, mxg_mv* X, const double* evals,
                             double* res, double* div);
+/* MxMagWaveOp::Apply (MxMagWaveOp.cpp:825-943): Y = P (L - sigma M)^-1 M X with L = vec_lapl, M = diag(m_diag) and the
+ * divergence-cleaning projection P b = b + gradPsi scaLapl^-1 divB M b (has_curl_null != 0). Both inner solves are
+ * block preconditioned CG on the GPU (vec_prec / sca_prec: multigrid handles or NULL; NULL scalar preconditioner = Jacobi).
+ * Valid for sigma below the lowest eigenvalue (the reference's automatic shift). info[0]/[1]: CG iterations. */
+int mxs_magwave_apply(mxg_ctx* ctx, mxg_crs* vec_lapl, mxg_mv* m_diag, mxg_crs* divB, mxg_crs* gradPsi, mxg_crs* scaLapl,
+                      mxg_gmg* vec_prec, mxg_gmg* sca_prec, double shift, double lin_tol, int has_curl_null,
+                      mxg_mv* X, mxg_mv* Y, int64_t info[2]);
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,7 @@ def load_library():
         "mxg_crs_row_map": (vp, [vp]),
         "mxg_crs_domain_map": (vp, [vp]),
         "mxg_mv_diag_mult": (i32, [vp, vp, vp]),
+        "mxg_crs_jacobi": (i32, [vp, vp, vp]),
         "mxg_gmg_default_params": (None, [vp]),
         "mxg_gmg_create": (i32, [vp, i32, vp, vp, vp, vp, pvp]),
         "mxg_gmg_destroy": (i32, [vp]),
@@ -141,6 +142,10 @@ def load_solver():
     S.mxs_lobpcg.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, dp]
     S.mxs_check_eigensolution.restype = C.c_int
     S.mxs_check_eigensolution.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    S.mxs_magwave_apply.restype = C.c_int
+    S.mxs_magwave_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp, vp]
+    S.mxs_last_profile.restype = None
+    S.mxs_last_profile.argtypes = [vp]
     _SOLVER = S
     return S
 
@@ -579,3 +584,27 @@ class MxSolver:
         if rc != 0:
             raise MxError(self._S.mxs_last_error().decode())
         return res, div
+
+
+class MxMagWaveOp:
+    """The shift-invert operator the reference hands to Anasazi (src/MxMagWaveOp.cpp:825-943):
+    y = P (L - sigma M)^-1 M x, with the divergence-cleaning projection P. Inner solves: block PCG on the GPU."""
+
+    def __init__(self, ctx, vec_lapl, m_diag, div_b=None, grad_psi=None, sca_lapl=None, vec_prec=None, sca_prec=None,
+                 shift=0.0, lin_tol=1e-10):
+        self._S = load_solver()
+        self.ctx, self.L, self.m, self.D, self.G, self.S = ctx, vec_lapl, m_diag, div_b, grad_psi, sca_lapl
+        self.vec_prec, self.sca_prec, self.shift, self.lin_tol = vec_prec, sca_prec, float(shift), float(lin_tol)
+        self.has_curl_null = div_b is not None
+        self.num_vec_lin_iters = self.num_sca_lin_iters = self.num_applies = 0
+
+    def Apply(self, x, y):
+        h = lambda o: o.h if o is not None else None
+        info = (C.c_int64 * 2)()
+        rc = self._S.mxs_magwave_apply(self.ctx.h, self.L.h, self.m.h, h(self.D), h(self.G), h(self.S), h(self.vec_prec),
+                                       h(self.sca_prec), self.shift, self.lin_tol, int(self.has_curl_null), x.h, y.h, info)
+        if rc != 0:
+            raise MxError(self._S.mxs_last_error().decode())
+        self.num_applies += 1
+        self.num_vec_lin_iters += info[0]
+        self.num_sca_lin_iters += info[1]

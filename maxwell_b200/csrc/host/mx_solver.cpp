@@ -108,3 +108,30 @@ int mxs_check_eigensolution(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_crs* d
 }
 
 }  // extern "C"
+
+// MxMagWaveOp::Apply (reference src/MxMagWaveOp.cpp:825-943): Y = P (L - sigma M)^-1 M X.
+// info[0] = vector-solve CG iterations, info[1] = scalar-solve CG iterations.
+extern "C" int mxs_magwave_apply(mxg_ctx* ctx, mxg_crs* vecLapl, mxg_mv* m_diag, mxg_crs* divB, mxg_crs* gradPsi, mxg_crs* scaLapl,
+                                 mxg_gmg* vecPrec, mxg_gmg* scaPrec, double shift, double linTol, int hasCurlNull,
+                                 mxg_mv* X, mxg_mv* Y, int64_t info[2]) {
+  try {
+    if (!ctx || !vecLapl || !m_diag || !X || !Y) throw std::runtime_error("mxs_magwave_apply: NULL argument");
+    if (hasCurlNull && (!divB || !gradPsi || !scaLapl)) throw std::runtime_error("mxs_magwave_apply: projection operators missing");
+    Wrapped w = wrap(ctx, X);
+    MxAnasaziMV<double> Xmv(X, w.map, false), Ymv(Y, w.map, false);
+    std::unique_ptr<MxGeoMultigridPrec<double>> Tv, Ts;
+    if (vecPrec) Tv.reset(new MxGeoMultigridPrec<double>(vecPrec, false));
+    if (scaPrec) Ts.reset(new MxGeoMultigridPrec<double>(scaPrec, false));
+    MxMagWaveOpParams p;
+    p.shift = shift;
+    p.linTol = linTol;
+    p.hasCurlNull = hasCurlNull != 0;
+    MxMagWaveOp op(vecLapl, m_diag, divB, gradPsi, scaLapl, Tv.get(), Ts.get(), p);
+    op.Apply(Xmv, Ymv);
+    if (info) { info[0] = op.numVecLinIters; info[1] = op.numScaLinIters; }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}

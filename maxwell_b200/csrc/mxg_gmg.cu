@@ -365,3 +365,21 @@ int mxg_mv_diag_mult(mxg_mv* y, const mxg_mv* d, const mxg_mv* x) {
 }
 
 }  // extern "C"
+
+// y = D^-1 x with D = diag(A): Jacobi preconditioner for the scalar-Laplacian projection solve
+// (the reference uses ML/ILUT there, MxMagWaveOp.cpp:285-537)
+extern "C" int mxg_crs_jacobi(const mxg_crs* A, const mxg_mv* x, mxg_mv* y) {
+  MXG_REQUIRE(A && x && y, "mxg_crs_jacobi: NULL argument");
+  MXG_REQUIRE(A->dInvDiag != nullptr, "mxg_crs_jacobi: operator is not square on one map");
+  MXG_REQUIRE(x->ld == A->nRows && y->ld == A->nRows && x->ncols == y->ncols, "mxg_crs_jacobi: shape mismatch");
+  MXG_REQUIRE(x->isComplex == A->isComplex && y->isComplex == A->isComplex, "mxg_crs_jacobi: mixed real/complex operands");
+  mxg_ctx* ctx = A->ctx;
+  if (x->ld == 0) return MXG_OK;
+  MXG_CUDA(cudaSetDevice(ctx->device));
+  if (A->isComplex)
+    k_diag_scale<zd><<<gridCols(ctx, x->ld, x->ncols), kBlock, 0, ctx->stream>>>(tableOf<zd>(y), tableOf<zd>(x), static_cast<const zd*>(A->dInvDiag), x->ld);
+  else
+    k_diag_scale<double><<<gridCols(ctx, x->ld, x->ncols), kBlock, 0, ctx->stream>>>(tableOf<double>(y), tableOf<double>(x), static_cast<const double*>(A->dInvDiag), x->ld);
+  LAUNCH_CHECK(ctx);
+  return MXG_OK;
+}
