@@ -146,6 +146,13 @@ class MxMultiVector {
     return std::make_shared<const MxVector<Scalar>>(*this, vecIndex, copy);
   }
 
+  // exchange the underlying storage of two multivectors of the same shape (no data movement)
+  void swap(MxMultiVector<Scalar>& other) {
+    std::swap(map_, other.map_);
+    std::swap(mv_, other.mv_);
+    std::swap(own_, other.own_);
+  }
+
   mxg_mv* getRawMV() const { return mv_; }   // the reference exposes the Epetra object the same way (MxMultiVector.hpp:85-89)
 
  protected:

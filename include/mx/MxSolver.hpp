@@ -263,6 +263,8 @@ class MxSolver {
     std::shared_ptr<MxMap> map = X.getMap();
     // S = [X | W | P] and its images under A and M live in three 3m-column allocations; views pick blocks
     MV Sb(map, 3 * m), ASb(map, 3 * m), MSb(map, 3 * m), tmp(map, 2 * m);
+    // second set: the Rayleigh-Ritz update writes X_new / P_new straight into it and the sets swap roles (no copy-back)
+    MV Sb2(map, 3 * m), ASb2(map, 3 * m), MSb2(map, 3 * m);
     auto range = [](int b, int n) { std::vector<int> v(n); std::iota(v.begin(), v.end(), b); return v; };
     auto view = [&](MV& base, const std::vector<int>& cols) { return std::unique_ptr<MV>(static_cast<MV*>(base.CloneViewNonConst(cols))); };
     auto timeit = [&](double& acc, auto&& f) {
@@ -441,8 +443,40 @@ class MxSolver {
         sc.insert(sc.end(), wc.begin(), wc.end());
         if (np > 0) { const std::vector<int> pcc = range(2 * m, np); sc.insert(sc.end(), pcc.begin(), pcc.end()); }
         ns = int(sc.size());
-        Dense GA = gram(Sb, sc, ASb, sc), GM = gram(Sb, sc, MSb, sc);
-        std::vector<double> ga = toVec(GA), gm = toVec(GM);
+        std::vector<double> ga, gm;
+        const int nwb = int(wc.size());
+        if (it % 10 == 0) {
+          // explicit Gram matrices of the whole basis (also resets the round-off drift of the implicit ones)
+          Dense GA = gram(Sb, sc, ASb, sc), GM = gram(Sb, sc, MSb, sc);
+          ga = toVec(GA);
+          gm = toVec(GM);
+        } else {
+          // implicit blocks: X^T A X = Theta, X^T M X = W^T M W = P^T M P = I, X^T M W = 0 by construction;
+          // only the columns belonging to W and P are computed (8 m^2 instead of 18 m^2 inner products)
+          std::vector<int> wpc2 = wc, xw = xc;
+          xw.insert(xw.end(), wc.begin(), wc.end());
+          if (np > 0) { const std::vector<int> pcc = range(2 * m, np); wpc2.insert(wpc2.end(), pcc.begin(), pcc.end()); }
+          const int nwp = int(wpc2.size());
+          Dense GA1 = gram(Sb, sc, ASb, wpc2);                    // ns x (nw + np)
+          ga.assign(size_t(ns) * ns, 0.0);
+          gm.assign(size_t(ns) * ns, 0.0);
+          for (int j = 0; j < m; ++j) ga[j + size_t(j) * ns] = theta[j];
+          for (int j = 0; j < ns; ++j) gm[j + size_t(j) * ns] = 1.0;
+          for (int j = 0; j < nwp; ++j)
+            for (int i = 0; i < ns; ++i) {
+              ga[i + size_t(m + j) * ns] = GA1(i, j);
+              if (i < m) ga[(m + j) + size_t(i) * ns] = GA1(i, j);
+            }
+          if (np > 0) {
+            const std::vector<int> pcc = range(2 * m, np);
+            Dense GM1 = gram(Sb, xw, MSb, pcc);                   // (m + nw) x np
+            for (int j = 0; j < np; ++j)
+              for (int i = 0; i < m + nwb; ++i) {
+                gm[i + size_t(m + nwb + j) * ns] = GM1(i, j);
+                gm[(m + nwb + j) + size_t(i) * ns] = GM1(i, j);
+              }
+          }
+        }
         for (int j = 0; j < ns; ++j)
           for (int i = 0; i < j; ++i) {
             ga[i + size_t(j) * ns] = ga[j + size_t(i) * ns] = 0.5 * (ga[i + size_t(j) * ns] + ga[j + size_t(i) * ns]);
@@ -464,17 +498,16 @@ class MxSolver {
       sc.insert(sc.end(), wc.begin(), wc.end());
       if (np > 0) { const std::vector<int> pcc = range(2 * m, np); sc.insert(sc.end(), pcc.begin(), pcc.end()); wpc.insert(wpc.end(), pcc.begin(), pcc.end()); }
       const std::vector<int> pnew = range(2 * m, m);
-      for (MV* base : {&Sb, &ASb, &MSb}) timeit(res.tUpdate, [&] {
-        auto s = view(*base, sc);
-        auto wp = view(*base, wpc);
-        auto tx = view(tmp, range(0, m));
-        auto tp = view(tmp, range(m, m));
+      MV* cur[3] = {&Sb, &ASb, &MSb};
+      MV* alt[3] = {&Sb2, &ASb2, &MSb2};
+      for (int t = 0; t < 3; ++t) timeit(res.tUpdate, [&] {
+        auto s = view(*cur[t], sc);
+        auto wp = view(*cur[t], wpc);
+        auto tx = view(*alt[t], xc);
+        auto tp = view(*alt[t], pnew);
         tx->MvTimesMatAddMv(1.0, *s, Cx, 0.0);
         tp->MvTimesMatAddMv(1.0, *wp, Cp, 0.0);
-        auto xdst = view(*base, xc);
-        auto pdst = view(*base, pnew);
-        *xdst = *tx;
-        *pdst = *tp;
+        cur[t]->swap(*alt[t]);
       });
       np = m;
       for (int j = 0; j < m; ++j) theta[j] = w[j];

@@ -516,7 +516,6 @@ template <class T>
 int applyImpl(const mxg_crs* A, const mxg_mv* x, mxg_mv* y, const Epilogue<T>& ep) {
   mxg_ctx* ctx = A->ctx;
   const int nvec = x->ncols;
-  constexpr int w = sizeof(T) / sizeof(double);
   const int64_t gTot = A->gLo + A->gHi;
   const bool halo = ctx->nranks > 1 && (gTot > 0 || A->sendTotal > 0);
   MXG_REQUIRE(*ctx->hErr == 0, "mxg_crs_apply: a previous halo exchange timed out waiting for a neighbour rank");
