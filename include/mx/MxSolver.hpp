@@ -577,6 +577,24 @@ class MxMagWaveOp : public mx::Operator<double> {
     y2.MvAddMv(1.0, y2, 1.0, bWork);                                                        // y += bWork (:921)
   }
 
+  // E = [invEps] curlB B (MxMagWaveOp.cpp:1237-1250). invEps may be NULL (no dielectric).
+  static void magToElec(mxg_crs* curlB, mxg_crs* invEps, const MV& mag, MV& elec) {
+    if (!invEps) { mx::check(mxg_crs_apply(curlB, mag.getRawMV(), elec.getRawMV())); return; }
+    MV d(elec.getMap(), elec.GetNumberVecs());
+    mx::check(mxg_crs_apply(curlB, mag.getRawMV(), d.getRawMV()));
+    mx::check(mxg_crs_apply(invEps, d.getRawMV(), elec.getRawMV()));
+  }
+  // eigenvalue of the (possibly shift-inverted) operator -> frequency in Hz (MxMagWaveOp.cpp:1252-1271)
+  static void eigValsToFreqs(const std::vector<std::complex<double>>& eigVals, std::vector<std::complex<double>>& freqs,
+                             double shift, bool invert) {
+    const double lightspeed = 299792458., pi = 3.14159265358979323846;   // MxUtil.hpp:23-24
+    freqs.resize(eigVals.size());
+    for (size_t i = 0; i < eigVals.size(); ++i) {
+      std::complex<double> k2 = invert ? 1.0 / eigVals[i] + shift : eigVals[i] + shift;
+      freqs[i] = std::sqrt(k2) * lightspeed / 2.0 / pi;
+    }
+  }
+
  private:
   void applyShifted(const MV& in, MV& out) const {   // out = (L - sigma M) in
     mx::check(mxg_crs_apply(L_, in.getRawMV(), out.getRawMV()));

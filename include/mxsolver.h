@@ -41,6 +41,11 @@ int mxs_check_eigensolution(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_crs* d
 int mxs_magwave_apply(mxg_ctx* ctx, mxg_crs* vec_lapl, mxg_mv* m_diag, mxg_crs* divB, mxg_crs* gradPsi, mxg_crs* scaLapl,
                       mxg_gmg* vec_prec, mxg_gmg* sca_prec, double shift, double lin_tol, int has_curl_null,
                       mxg_mv* X, mxg_mv* Y, int64_t info[2]);
+/* MxMagWaveOp::magToElec (MxMagWaveOp.cpp:1237-1250): elec = [invEps] curlB mag; invEps NULL when there is no dielectric. */
+int mxs_mag_to_elec(mxg_ctx* ctx, mxg_crs* curlB, mxg_crs* invEps, mxg_mv* mag, mxg_mv* elec);
+/* MxMagWaveOp::eigValsToFreqs (MxMagWaveOp.cpp:1252-1271): f = sqrt(k2) c / 2 pi [Hz], k2 = ev + shift, or 1/ev + shift for the
+ * shift-inverted operator. im may be NULL (real eigenvalues). Host arithmetic. */
+int mxs_eigvals_to_freqs(const double* re, const double* im, int n, double shift, int invert, double* fre, double* fim);
 #ifdef __cplusplus
 }
 #endif

@@ -142,6 +142,10 @@ def load_solver():
     S.mxs_lobpcg.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, dp]
     S.mxs_check_eigensolution.restype = C.c_int
     S.mxs_check_eigensolution.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    S.mxs_mag_to_elec.restype = C.c_int
+    S.mxs_mag_to_elec.argtypes = [vp, vp, vp, vp, vp]
+    S.mxs_eigvals_to_freqs.restype = C.c_int
+    S.mxs_eigvals_to_freqs.argtypes = [vp, vp, C.c_int, C.c_double, C.c_int, vp, vp]
     S.mxs_magwave_apply.restype = C.c_int
     S.mxs_magwave_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp, vp]
     S.mxs_last_profile.restype = None
@@ -608,3 +612,22 @@ class MxMagWaveOp:
         self.num_applies += 1
         self.num_vec_lin_iters += info[0]
         self.num_sca_lin_iters += info[1]
+
+
+def mag_to_elec(ctx, curl_b, inv_eps, mag, elec):
+    """MxMagWaveOp::magToElec (src/MxMagWaveOp.cpp:1237-1250): elec = [invEps] curlB mag."""
+    S = load_solver()
+    if S.mxs_mag_to_elec(ctx.h, curl_b.h, inv_eps.h if inv_eps is not None else None, mag.h, elec.h) != 0:
+        raise MxError(S.mxs_last_error().decode())
+
+
+def eigvals_to_freqs(eigvals, shift=0.0, invert=False):
+    """MxMagWaveOp::eigValsToFreqs (src/MxMagWaveOp.cpp:1252-1271): complex frequencies in Hz."""
+    S = load_solver()
+    ev = np.ascontiguousarray(np.asarray(eigvals, dtype=np.complex128))
+    re, im = np.ascontiguousarray(ev.real), np.ascontiguousarray(ev.imag)
+    fre, fim = np.empty_like(re), np.empty_like(re)
+    if S.mxs_eigvals_to_freqs(re.ctypes.data, im.ctypes.data, len(re), float(shift), int(invert), fre.ctypes.data,
+                              fim.ctypes.data) != 0:
+        raise MxError(S.mxs_last_error().decode())
+    return fre + 1j * fim

@@ -135,3 +135,32 @@ extern "C" int mxs_magwave_apply(mxg_ctx* ctx, mxg_crs* vecLapl, mxg_mv* m_diag,
     return -1;
   }
 }
+
+// MxMagWaveOp::magToElec (reference src/MxMagWaveOp.cpp:1237-1250): E = [invEps] curlB B. invEps NULL = vacuum.
+extern "C" int mxs_mag_to_elec(mxg_ctx* ctx, mxg_crs* curlB, mxg_crs* invEps, mxg_mv* mag, mxg_mv* elec) {
+  try {
+    if (!ctx || !curlB || !mag || !elec) throw std::runtime_error("mxs_mag_to_elec: NULL argument");
+    Wrapped wm = wrap(ctx, mag), we = wrap(ctx, elec);
+    MxAnasaziMV<double> B(mag, wm.map, false), E(elec, we.map, false);
+    MxMagWaveOp::magToElec(curlB, invEps, B, E);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// MxMagWaveOp::eigValsToFreqs (reference src/MxMagWaveOp.cpp:1252-1271); host arithmetic only.
+extern "C" int mxs_eigvals_to_freqs(const double* re, const double* im, int n, double shift, int invert, double* fre, double* fim) {
+  try {
+    if (n < 0 || (n > 0 && (!re || !fre || !fim))) throw std::runtime_error("mxs_eigvals_to_freqs: bad argument");
+    std::vector<std::complex<double>> ev(n), fr;
+    for (int i = 0; i < n; ++i) ev[i] = std::complex<double>(re[i], im ? im[i] : 0.0);
+    MxMagWaveOp::eigValsToFreqs(ev, fr, shift, invert != 0);
+    for (int i = 0; i < n; ++i) { fre[i] = fr[i].real(); fim[i] = fr[i].imag(); }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}

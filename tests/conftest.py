@@ -44,7 +44,7 @@ def gpu_matrix(mx, ctx, sim, name, layout=None, is_complex=None):
     fields = {"curlCurl": ("bfield", "bfield"), "vecLapl": ("bfield", "bfield"), "gradDiv": ("bfield", "bfield"),
               "mRhs": ("bfield", "bfield"), "dmA": ("bfield", "bfield"), "curlE": ("bfield", "efield"),
               "curlB": ("efield", "bfield"), "divB": ("psifield", "bfield"), "gradPsi": ("bfield", "psifield"),
-              "scaLapl": ("psifield", "psifield")}[name]
+              "scaLapl": ("psifield", "psifield"), "invEps": ("efield", "dfield")}[name]
     rmap = mx.MxMap(ctx, sim.num_global(fields[0]), rg)
     cmap = rmap if fields[0] == fields[1] else mx.MxMap(ctx, sim.num_global(fields[1]), cg)
     A = mx.MxCrsMatrix.from_csr(rmap, cmap, rowptr, cg[col], val, layout=layout)

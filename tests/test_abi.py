@@ -61,3 +61,30 @@ def test_hash_uniform_range(mx):
     assert v.min() >= -1.0 and v.max() < 1.0
     assert abs(v.mean()) < 0.01 and abs(v.std() - 1 / np.sqrt(3)) < 0.01
     assert not np.array_equal(v, mx.hash_uniform(12345, np.arange(100000), 1))
+
+
+def test_solver_header_symbols_are_exported(mx):
+    """libmxsolver.so exports everything include/mxsolver.h declares."""
+    text = open(os.path.join(ROOT, "include", "mxsolver.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(mxs_[a-z0-9_]+)\s*\(", text)))
+    assert len(syms) >= 8
+    S = mx.load_solver()
+    for s in syms:
+        assert hasattr(S, s), s
+
+
+def test_eigvals_to_freqs(mx):
+    """MxMagWaveOp::eigValsToFreqs (src/MxMagWaveOp.cpp:1252-1271): f = sqrt(ev + shift) c / 2 pi, or with 1/ev when
+    the eigenvalue belongs to the shift-inverted operator. Pure host arithmetic, no GPU."""
+    import numpy as np
+    c = 299792458.0
+    k2 = np.array([15.42, 21.19, 36.14, -1e-9])
+    f = mx.eigvals_to_freqs(k2)
+    np.testing.assert_allclose(f[:3].real, np.sqrt(k2[:3]) * c / (2 * np.pi), rtol=1e-15)
+    assert np.all(f[:3].imag == 0) and f[3].real < 1e-3 and f[3].imag > 0   # slightly negative k^2 -> imaginary f
+    shift = 10.0
+    mu = 1.0 / (k2[:3] - shift)                                               # eigenvalues of (A - shift)^-1
+    f2 = mx.eigvals_to_freqs(mu, shift=shift, invert=True)
+    np.testing.assert_allclose(f2.real, f[:3].real, rtol=1e-13)
+    assert mx.eigvals_to_freqs([]).shape == (0,)

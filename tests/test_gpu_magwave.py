@@ -53,3 +53,21 @@ def test_shift_invert_apply_on_eigenvectors(mx, ctx, orc):
     d = mx.MxMultiVector(pmap, 2)
     D.apply(My, d)
     assert d.norm2().max() < 1e-7 * My.norm2().max() * 24
+
+
+@pytest.mark.parametrize("config", ["pillbox", "dsphmsph"])
+def test_mag_to_elec(mx, ctx, orc, config):
+    """MxMagWaveOp::magToElec (src/MxMagWaveOp.cpp:1237-1250): E = [invEps] curlB B, bit-identical to the oracle chain."""
+    sim = orc.pillbox(16) if config == "pillbox" else orc.dsphmsph(16)
+    Cb, opC, emap, bmap = gpu_matrix(mx, ctx, sim, "curlB")
+    Ie = opI = None
+    if config == "dsphmsph":
+        Ie, opI, emap2, dmap = gpu_matrix(mx, ctx, sim, "invEps")
+    mag = mx.MxMultiVector(bmap, 3)
+    mag.random(17)
+    elec = mx.MxMultiVector(emap, 3)
+    mx.mag_to_elec(ctx, Cb, Ie, mag, elec)
+    want = opC.apply(mag.to_host())
+    if opI is not None:
+        want = opI.apply(want)
+    assert np.array_equal(elec.to_host(), want)
