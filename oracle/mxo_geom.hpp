@@ -33,19 +33,86 @@ inline D3 cross(const D3& a, const D3& b) {
 inline int sgn(double v) { return v < 0.0 ? -1 : (v > 0.0 ? 1 : 0); }
 
 // ---------------------------------------------------------------------------------------
-// Shapes: f > 0 inside (MxShape.hpp:143-165). Only translations are supported here
-// (A = I), which is all the BASELINE configs use; func(p) = sign * f0(p - b).
+// Shapes: f > 0 inside. MxShape.hpp:143-165: func(p) = sign * f0(Ainv p - Ainv b) with the
+// affine placement x -> A x + b built up by translate / reflect (MxShape.cpp:172-210).
+// Rotations and scalings are not restated (no BASELINE config uses them).
 // ---------------------------------------------------------------------------------------
+using R33 = std::array<std::array<double, 3>, 3>;
+inline R33 r33Eye() { return {{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}}; }
+inline D3 operator*(const R33& m, const D3& v) {
+  D3 r;
+  for (int i = 0; i < 3; ++i) r[i] = m[i][0] * v[0] + m[i][1] * v[1] + m[i][2] * v[2];
+  return r;
+}
+inline D3 rowTimes(const D3& v, const R33& m) {   // v^T M (MxDimVector * MxDimMatrix)
+  D3 r;
+  for (int j = 0; j < 3; ++j) r[j] = v[0] * m[0][j] + v[1] * m[1][j] + v[2] * m[2][j];
+  return r;
+}
+inline R33 operator*(const R33& x, const R33& y) {
+  R33 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r[i][j] = x[i][0] * y[0][j] + x[i][1] * y[1][j] + x[i][2] * y[2][j];
+  return r;
+}
+inline R33 operator*(double s, const R33& m) {
+  R33 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r[i][j] = s * m[i][j];
+  return r;
+}
+// The reference inverts with LAPACK GESV (MxDimMatrix.hpp:242-256); the cofactor form gives the same
+// exact result for the signed permutation / reflection matrices the configs produce.
+inline R33 r33Inv(const R33& a) {
+  const double det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+                     a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+  R33 r;
+  r[0][0] = (a[1][1] * a[2][2] - a[1][2] * a[2][1]) / det;
+  r[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) / det;
+  r[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) / det;
+  r[1][0] = (a[1][2] * a[2][0] - a[1][0] * a[2][2]) / det;
+  r[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) / det;
+  r[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) / det;
+  r[2][0] = (a[1][0] * a[2][1] - a[1][1] * a[2][0]) / det;
+  r[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) / det;
+  r[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) / det;
+  return r;
+}
+// P = I - a a^T for a unit axis (the "complementary axis projection" of cylinder / torus / cone)
+inline R33 complAxisProj(const D3& a) {
+  R33 P = r33Eye();
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) P[i][j] -= a[i] * a[j];
+  return P;
+}
+
 struct Shape {
   double sign = 1.0;
-  D3 b{0, 0, 0};
+  D3 b{0, 0, 0}, Ainvb{0, 0, 0};
+  R33 A = r33Eye(), Ainv = r33Eye();
   virtual ~Shape() {}
   virtual double f0(const D3& p) const = 0;
   virtual D3 g0(const D3& p) const = 0;
-  double func(const D3& p) const { return sign * f0(p - b); }
-  D3 grad(const D3& p) const { return sign * g0(p - b); }
-  void translate(const D3& v) { b = b + v; }
+  virtual std::shared_ptr<Shape> clone() const = 0;   // copy; composite shapes keep sharing their parts
+  double func(const D3& p) const { return sign * f0(Ainv * p - Ainvb); }
+  D3 grad(const D3& p) const { return sign * rowTimes(g0(Ainv * p - Ainvb), Ainv); }
+  void translate(const D3& v) {   // MxShape.cpp:179-185
+    b = b + v;
+    Ainvb = Ainv * b;
+  }
+  void reflect(const D3& normal, const D3& pointInPlane) {   // MxShape.cpp:196-210
+    const D3 n = normal / norm(normal);
+    R33 M = r33Eye();
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) M[i][j] -= 2.0 * (n[i] * n[j]);
+    A = M * A;
+    b = M * (b - pointInPlane) + pointInPlane;
+    Ainv = r33Inv(A);
+    Ainvb = Ainv * b;
+  }
+  void invert() { sign *= -1.0; }
 };
+#define MXO_CLONE(T) std::shared_ptr<Shape> clone() const override { return std::make_shared<T>(*this); }
 
 // MxCylinder.hpp:34-40,74-84: f = r^2 - p.(P p), P = I - a a^T.
 struct Cylinder : Shape {
@@ -68,6 +135,7 @@ struct Cylinder : Shape {
   }
   double f0(const D3& p) const override { return r2 - dot(p, Pp(p)); }
   D3 g0(const D3& p) const override { return -2.0 * Pp(p); }
+  MXO_CLONE(Cylinder)
 };
 
 // MxHalfSpace.hpp:31-33: f = n.p
@@ -76,6 +144,7 @@ struct HalfSpace : Shape {
   HalfSpace(D3 pointInPlane, D3 normal) : n(normal / norm(normal)) { translate(pointInPlane); }
   double f0(const D3& p) const override { return dot(n, p); }
   D3 g0(const D3&) const override { return n; }
+  MXO_CLONE(HalfSpace)
 };
 
 // MxSphere.hpp:31-33: f = 1 - p.p / r^2
@@ -84,6 +153,7 @@ struct Sphere : Shape {
   Sphere(double r, D3 loc) : r2(r * r) { translate(loc); }
   double f0(const D3& p) const override { return 1.0 - dot(p, p) / r2; }
   D3 g0(const D3& p) const override { return -2.0 * p / r2; }
+  MXO_CLONE(Sphere)
 };
 
 // MxShapeIntersection.hpp:120-136 (min of sub-shape funcs), :186-206 (gradient of the
@@ -107,6 +177,7 @@ struct Intersection : Shape {
     }
     return arg->grad(p);
   }
+  MXO_CLONE(Intersection)
 };
 
 // MxSlab.hpp:33-39,95-100: two half-spaces at -/+ l/2 along n, then translated.
@@ -118,6 +189,119 @@ inline std::shared_ptr<Shape> makeSlab(double thickness, D3 n, D3 loc) {
   s->translate(loc);
   return s;
 }
+
+// MxTorus.hpp:31-37,51-65: f = r^2 - (R - |P p|)^2 - (a.p)^2. The gradient is restated literally: its in-plane
+// term carries the opposite sign of the true derivative (quirk R14); it only steers the Newton proposals of
+// rootFind, whose bisection safeguard still brackets the root.
+struct Torus : Shape {
+  D3 axis;
+  double R, r2;
+  R33 P;
+  Torus(double majorRadius, double minorRadius, D3 torusAxis, D3 loc)
+      : axis(torusAxis / norm(torusAxis)), R(majorRadius), r2(minorRadius * minorRadius), P(complAxisProj(axis)) {
+    translate(loc);
+  }
+  double f0(const D3& p) const override {
+    const double d = R - norm(P * p), h = dot(axis, p);
+    return r2 - d * d - h * h;
+  }
+  D3 g0(const D3& p) const override {
+    const double c = 1.0 - R / norm(P * p);
+    return 2.0 * (((c * P) * p) - dot(axis, p) * axis);
+  }
+  MXO_CLONE(Torus)
+};
+
+// MxCone.hpp:31-37,52-62: double cone about `axis` with half-angle theta, vertex at `vertex`.
+struct Cone : Shape {
+  D3 axis;
+  double tanTheta;
+  R33 P;
+  Cone(double angle, D3 coneAxis, D3 vertex) : axis(coneAxis / norm(coneAxis)), tanTheta(std::tan(angle)), P(complAxisProj(axis)) {
+    translate(vertex);
+  }
+  double f0(const D3& p) const override {
+    const double t = tanTheta * dot(axis, p);
+    return t * t - dot(p, P * p);
+  }
+  D3 g0(const D3& p) const override { return 2.0 * ((tanTheta * tanTheta * dot(axis, p)) * axis - P * p); }
+  MXO_CLONE(Cone)
+};
+
+// MxShapeUnion.hpp:62-78 (max of the sub-shape funcs), :135-154 (gradient of the first strict maximiser).
+struct Union : Shape {
+  std::vector<std::shared_ptr<Shape>> subs;
+  double f0(const D3& p) const override {
+    double fmax = -std::numeric_limits<double>::max();
+    for (auto& s : subs) {
+      const double f = s->func(p);
+      if (f > fmax) fmax = f;
+    }
+    return fmax;
+  }
+  D3 g0(const D3& p) const override {
+    double fmax = -std::numeric_limits<double>::max();
+    const Shape* arg = nullptr;
+    for (auto& s : subs) {
+      const double f = s->func(p);
+      if (f > fmax) { fmax = f; arg = s.get(); }
+    }
+    return arg->grad(p);
+  }
+  MXO_CLONE(Union)
+};
+
+// MxShapeSubtract.hpp:14-18,69-92,158-176: base minus an (inverted) union of removal shapes.
+struct Subtract : Shape {
+  std::shared_ptr<Shape> base;
+  Union rm;
+  Subtract() { rm.invert(); }
+  double f0(const D3& p) const override {
+    const double fBase = base->func(p), fRm = rm.func(p);
+    const bool inBase = fBase > 0, inRm = fRm < 0;
+    if (inRm && inBase) return fRm;
+    if (!inRm && !inBase) return fBase;
+    return fBase < fRm ? fBase : fRm;
+  }
+  D3 g0(const D3& p) const override {
+    const double fBase = base->func(p), fRm = rm.func(p);
+    const bool inBase = fBase > 0, inRm = fRm < 0;
+    if (inRm && inBase) return rm.grad(p);
+    if (!inRm && !inBase) return base->grad(p);
+    return fBase < fRm ? base->grad(p) : rm.grad(p);
+  }
+  MXO_CLONE(Subtract)
+};
+
+// MxShapeMirror.hpp:85-116,155-165: the shape on the positive side of the plane, its reflected clone elsewhere.
+struct Mirror : Shape {
+  std::shared_ptr<Shape> shape, mirrored;
+  HalfSpace plane;
+  Mirror(std::shared_ptr<Shape> s, D3 normal, D3 pointInPlane) : shape(s), plane(pointInPlane, normal / norm(normal)) {
+    mirrored = shape->clone();
+    mirrored->reflect(normal / norm(normal), pointInPlane);
+  }
+  double f0(const D3& p) const override { return plane.func(p) > 0.0 ? shape->func(p) : mirrored->func(p); }
+  D3 g0(const D3& p) const override { return plane.func(p) > 0.0 ? shape->grad(p) : mirrored->grad(p); }
+  MXO_CLONE(Mirror)
+};
+
+// MxShapeRepeat.hpp:84-118,138-148: fold p back into the base period along `dir`, clamped to [-numNeg, numPos] periods.
+struct Repeat : Shape {
+  std::shared_ptr<Shape> shape;
+  D3 o, dir;
+  double s, np, nn;
+  Repeat(std::shared_ptr<Shape> sh, D3 origin, D3 direction, double step, int numPos, int numNeg)
+      : shape(sh), o(origin), dir(direction / norm(direction)), s(step), np(numPos), nn(-numNeg) {}
+  D3 fold(const D3& p) const {
+    const double slabPt = dot(p - o, dir) / s + 0.5;
+    if (slabPt >= 0.0) return p - (s * std::min(std::floor(slabPt), np)) * dir;
+    return p - (s * std::max(std::floor(slabPt), nn)) * dir;
+  }
+  double f0(const D3& p) const override { return shape->func(fold(p)); }
+  D3 g0(const D3& p) const override { return shape->grad(fold(p)); }
+  MXO_CLONE(Repeat)
+};
 
 // ---------------------------------------------------------------------------------------
 // Safeguarded Newton / bisection on the segment p1->p2 (MxUtil.hpp:295-362). The

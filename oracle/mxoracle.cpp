@@ -41,6 +41,39 @@ void* mxo_shape_intersection(void* const* shapes, int n) {
   for (int i = 0; i < n; ++i) is->subs.push_back(*static_cast<std::shared_ptr<Shape>*>(shapes[i]));
   return new std::shared_ptr<Shape>(is);
 }
+static std::shared_ptr<Shape>& shp(void* h) { return *static_cast<std::shared_ptr<Shape>*>(h); }
+void* mxo_shape_torus(double majorRadius, double minorRadius, const double axis[3], const double loc[3]) {
+  return new std::shared_ptr<Shape>(new Torus(majorRadius, minorRadius, {axis[0], axis[1], axis[2]}, {loc[0], loc[1], loc[2]}));
+}
+void* mxo_shape_cone(double angle, const double axis[3], const double vertex[3]) {
+  return new std::shared_ptr<Shape>(new Cone(angle, {axis[0], axis[1], axis[2]}, {vertex[0], vertex[1], vertex[2]}));
+}
+void* mxo_shape_union(void* const* shapes, int n) {
+  auto u = std::make_shared<Union>();
+  for (int i = 0; i < n; ++i) u->subs.push_back(shp(shapes[i]));
+  return new std::shared_ptr<Shape>(u);
+}
+void* mxo_shape_subtract(void* base, void* const* removed, int n) {
+  auto d = std::make_shared<Subtract>();
+  d->base = shp(base);
+  for (int i = 0; i < n; ++i) d->rm.subs.push_back(shp(removed[i]));
+  return new std::shared_ptr<Shape>(d);
+}
+void* mxo_shape_mirror(void* shape, const double normal[3], const double point[3]) {
+  return new std::shared_ptr<Shape>(new Mirror(shp(shape), {normal[0], normal[1], normal[2]}, {point[0], point[1], point[2]}));
+}
+void* mxo_shape_repeat(void* shape, const double origin[3], const double dir[3], double step, int numPos, int numNeg) {
+  return new std::shared_ptr<Shape>(
+      new Repeat(shp(shape), {origin[0], origin[1], origin[2]}, {dir[0], dir[1], dir[2]}, step, numPos, numNeg));
+}
+void mxo_shape_translate(void* sh, const double v[3]) { shp(sh)->translate({v[0], v[1], v[2]}); }
+void mxo_shape_reflect(void* sh, const double normal[3], const double point[3]) {
+  shp(sh)->reflect({normal[0], normal[1], normal[2]}, {point[0], point[1], point[2]});
+}
+void mxo_shape_grad(void* sh, const double p[3], double g[3]) {
+  const D3 r = shp(sh)->grad({p[0], p[1], p[2]});
+  g[0] = r[0]; g[1] = r[1]; g[2] = r[2];
+}
 void mxo_shape_invert(void* sh) { (*static_cast<std::shared_ptr<Shape>*>(sh))->sign *= -1.0; }
 double mxo_shape_func(void* sh, const double p[3]) { return (*static_cast<std::shared_ptr<Shape>*>(sh))->func({p[0], p[1], p[2]}); }
 void mxo_shape_destroy(void* sh) { delete static_cast<std::shared_ptr<Shape>*>(sh); }

@@ -36,6 +36,15 @@ def lib():
             "mxo_shape_slab": (vp, [dbl, d3, d3]),
             "mxo_shape_halfspace": (vp, [d3, d3]),
             "mxo_shape_intersection": (vp, [C.POINTER(vp), C.c_int]),
+            "mxo_shape_torus": (vp, [dbl, dbl, d3, d3]),
+            "mxo_shape_cone": (vp, [dbl, d3, d3]),
+            "mxo_shape_union": (vp, [C.POINTER(vp), C.c_int]),
+            "mxo_shape_subtract": (vp, [vp, C.POINTER(vp), C.c_int]),
+            "mxo_shape_mirror": (vp, [vp, d3, d3]),
+            "mxo_shape_repeat": (vp, [vp, d3, d3, dbl, C.c_int, C.c_int]),
+            "mxo_shape_translate": (None, [vp, d3]),
+            "mxo_shape_reflect": (None, [vp, d3, d3]),
+            "mxo_shape_grad": (None, [vp, d3, d3]),
             "mxo_shape_invert": (None, [vp]),
             "mxo_shape_func": (dbl, [vp, d3]),
             "mxo_shape_destroy": (None, [vp]),
@@ -115,8 +124,53 @@ class Shape:
         arr = (C.c_void_p * len(shapes))(*[s.h for s in shapes])
         return Shape(lib().mxo_shape_intersection(arr, len(shapes)), keep=tuple(shapes))
 
+    @staticmethod
+    def torus(major_radius, minor_radius, axis, loc):
+        return Shape(lib().mxo_shape_torus(major_radius, minor_radius, _d3(axis), _d3(loc)))
+
+    @staticmethod
+    def cone(angle, axis, vertex):
+        return Shape(lib().mxo_shape_cone(angle, _d3(axis), _d3(vertex)))
+
+    @staticmethod
+    def union(shapes):
+        arr = (C.c_void_p * len(shapes))(*[s.h for s in shapes])
+        return Shape(lib().mxo_shape_union(arr, len(shapes)), keep=tuple(shapes))
+
+    @staticmethod
+    def subtract(base, removed):
+        removed = list(removed) if isinstance(removed, (list, tuple)) else [removed]
+        arr = (C.c_void_p * len(removed))(*[s.h for s in removed])
+        return Shape(lib().mxo_shape_subtract(base.h, arr, len(removed)), keep=(base,) + tuple(removed))
+
+    @staticmethod
+    def mirror(shape, normal, point):
+        return Shape(lib().mxo_shape_mirror(shape.h, _d3(normal), _d3(point)), keep=(shape,))
+
+    @staticmethod
+    def repeat(shape, origin, direction, step, num_pos, num_neg):
+        return Shape(lib().mxo_shape_repeat(shape.h, _d3(origin), _d3(direction), float(step), int(num_pos), int(num_neg)),
+                     keep=(shape,))
+
+    def translate(self, v):
+        lib().mxo_shape_translate(self.h, _d3(v))
+        return self
+
+    def reflect(self, normal, point):
+        lib().mxo_shape_reflect(self.h, _d3(normal), _d3(point))
+        return self
+
+    def invert(self):
+        lib().mxo_shape_invert(self.h)
+        return self
+
     def func(self, p):
         return lib().mxo_shape_func(self.h, _d3(p))
+
+    def grad(self, p):
+        g = (C.c_double * 3)()
+        lib().mxo_shape_grad(self.h, _d3(p), g)
+        return np.array(list(g))
 
     def fraction(self, kind, axis, lens, p):
         return lib().mxo_fraction(self.h, kind, axis, _d3(list(lens) + [0.0] * (3 - len(lens))), _d3(p))
@@ -291,6 +345,48 @@ def pillbox(n, radius=0.4, length=0.8, origin=-0.5, size=1.0):
     caps = Shape.slab(length, (0, 0, 1), (0, 0, 0))
     cav = Shape.intersection([cyl, caps])
     return Sim(n, origin=(origin,) * 3, size=(size,) * 3, pec=cav)
+
+
+def crabcav_shape(num_cells=4, cell_len=2.0 * 0.0192, cav_rad=0.04719, iris_rad=0.015, cav_rho=0.0136, iris_rho=0.00331):
+    """example/crabcav.py:13-66 -- the 4-cell crab cavity as CSG: per half cell (cone ∩ tube) ∪ equator torus ∪
+    (iris tube − iris torus), mirrored in z = 0, repeated along z and capped by a slab."""
+    import math
+    rho_sum = cav_rho + iris_rho
+    rad_diff = cav_rad - iris_rad
+    half2 = 0.25 * cell_len * cell_len
+    diff2 = (rad_diff - rho_sum) ** 2
+    cos_t = (rho_sum - rad_diff) * rho_sum
+    cos_t += math.sqrt(half2 * (diff2 - rho_sum * rho_sum + half2))
+    cos_t /= half2 + diff2
+    theta = math.acos(cos_t)
+    sin_t = math.sqrt(1 - cos_t * cos_t)
+    cot_t = 1.0 / (sin_t / cos_t)
+    cone_off = 0.5 * cell_len - iris_rho * sin_t + (iris_rad + iris_rho * (1.0 - cos_t)) * cot_t
+    zhat, o = (0, 0, 1), (0, 0, 0)
+    iris_tube = Shape.cylinder(iris_rad + iris_rho * (1.0 - cos_t), zhat, o)
+    iris_torus = Shape.torus(iris_rad + iris_rho, iris_rho, zhat, (0, 0, 0.5 * cell_len))
+    corr_iris_tube = Shape.subtract(iris_tube, iris_torus)
+    cav_tube = Shape.cylinder(cav_rad - cav_rho * (1.0 - cos_t), zhat, o)
+    cav_cone = Shape.cone(theta, zhat, (0, 0, cone_off))
+    cav_torus = Shape.torus(cav_rad - cav_rho, cav_rho, zhat, o)
+    pre_cav = Shape.intersection([cav_cone, cav_tube])
+    half_cell = Shape.union([pre_cav, cav_torus, corr_iris_tube])
+    full_cell = Shape.mirror(half_cell, zhat, o)
+    inf_cells = Shape.repeat(full_cell, o, zhat, cell_len, num_cells // 2, num_cells // 2)
+    caps = Shape.slab(float(num_cells) * cell_len, zhat, o)
+    return Shape.intersection([caps, inf_cells])
+
+
+def crabcav(cell_res=10, pad=2, num_cells=4, cell_len=2.0 * 0.0192, cav_rad=0.04719):
+    """example/crabcav.py:69-91: grid of cell_res cells per cavity cell along z plus `pad` cells of metal around."""
+    import math
+    delta = cell_len / float(cell_res)
+    nz = num_cells * cell_res + 2 * pad
+    lz = float(nz) * delta
+    nx = 2 * (int(math.ceil(cav_rad / delta)) + pad)
+    lx = float(nx) * delta
+    return Sim((nx, nx, nz), origin=(-0.5 * lx, -0.5 * lx, -0.5 * lz), size=(lx, lx, lz),
+               pec=crabcav_shape(num_cells=num_cells, cell_len=cell_len, cav_rad=cav_rad))
 
 
 def dsphmsph(n, eps=10.0, a=0.37, b=0.49, size=1.0, origin=-0.5):

@@ -11,6 +11,8 @@ fixtures are INDEPENDENT re-derivations, not reference outputs:
   vacuum_spectrum.npz      analytic eigenvalues sum_i (2/h_i sin(pi m_i/N_i))^2
   pillbox_counts.npz       map sizes / nnz of the pillbox operators at N=12,20 as produced by
                            the oracle at the commit that introduced it (regression pin)
+  crabcav_counts.npz       same for the crab-cavity CSG config (cell_res 8), plus the sums of the
+                           face / edge / volume fractions
 """
 import os
 import sys
@@ -73,6 +75,12 @@ def main():
         row += [sim.op(o).nnz for o in ("curlCurl", "gradDiv", "vecLapl", "scaLapl")]
         counts["n%d" % N] = np.asarray(row, dtype=np.int64)
     np.savez_compressed(os.path.join(HERE, "pillbox_counts.npz"), **counts)
+    sim = orc.crabcav(cell_res=8, pad=2)
+    row = [len(sim.map(f)) for f in ("bfield", "efield", "psifield")]
+    row += [sim.op(o).nnz for o in ("curlCurl", "gradDiv", "vecLapl", "scaLapl")]
+    sums = [sim.fracs(f).sum() for f in ("bfield", "efield", "psifield")]
+    np.savez_compressed(os.path.join(HERE, "crabcav_counts.npz"), counts=np.asarray(row, dtype=np.int64),
+                        frac_sums=np.asarray(sums))
 
 
 if __name__ == "__main__":
