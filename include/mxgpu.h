@@ -133,6 +133,11 @@ int mxg_mv_download(const mxg_mv* mv, double* host, int64_t ld);
 mxg_map* mxg_mv_get_map(const mxg_mv* mv);
 mxg_map* mxg_crs_row_map(const mxg_crs* A);
 mxg_map* mxg_crs_domain_map(const mxg_crs* A);
+/* Field output in the layout of MxIO::save (MxIO.cpp:166-221): column `col` scattered into a dense array over the
+ * GID range [gid_lo, gid_hi) -- GID = comp + numComps * cell, cell z-fastest over the node grid (MxGrid.h:96-114) --
+ * with zeros where the map holds no DOF. Host buffers of gid_hi - gid_lo doubles; out_imag only for complex fields.
+ * A slab rank passes the GID range of its own planes. */
+int mxg_mv_to_grid(const mxg_mv* mv, int col, int64_t gid_lo, int64_t gid_hi, double* out_real, double* out_imag);
 /* device pointer of column j (for host code that enqueues its own kernels) */
 void* mxg_mv_col_ptr(mxg_mv* mv, int j);
 

@@ -83,6 +83,7 @@ def load_library():
         "mxg_mv_times_mat_add_mv": (i32, [dp, vp, vp, i32, dp, vp]),
         "mxg_mv_upload": (i32, [vp, vp, i64]),
         "mxg_mv_download": (i32, [vp, vp, i64]),
+        "mxg_mv_to_grid": (i32, [vp, i32, i64, i64, vp, vp]),
         "mxg_mv_col_ptr": (vp, [vp, i32]),
         "mxg_crs_create": (i32, [vp, vp, vp, vp, vp, i32, pvp]),
         "mxg_crs_create_opts": (i32, [vp, vp, vp, vp, vp, i32, i32, pvp]),
@@ -372,6 +373,15 @@ class MxMultiVector:
             out = np.empty((n, b), dtype=self.dtype, order="F")
         _ck(self._L.mxg_mv_download(self.h, out.ctypes.data, n))
         return out
+
+    def to_grid(self, col, gid_lo, gid_hi):
+        """Column `col` in the dense [cell][comp] layout MxIO::save writes (src/MxIO.cpp:166-221), zeros at masked DOFs."""
+        n = int(gid_hi) - int(gid_lo)
+        re = np.empty(n, dtype=np.float64)
+        im = np.empty(n, dtype=np.float64) if self.is_complex else None
+        _ck(self._L.mxg_mv_to_grid(self.h, int(col), int(gid_lo), int(gid_hi), re.ctypes.data,
+                                   im.ctypes.data if im is not None else None))
+        return re + 1j * im if im is not None else re
 
     def col_ptr(self, j):
         return self._L.mxg_mv_col_ptr(self.h, j)

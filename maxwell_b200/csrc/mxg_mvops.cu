@@ -494,6 +494,18 @@ int checkSame(const char* fn, const mxg_mv* a, const mxg_mv* b, bool sameCols = 
 
 }  // namespace
 
+// Field output layout of MxIO::save (reference src/MxIO.cpp:166-221): a dense [cell][comp] array over the node grid, zero
+// where the map holds no DOF. The global component index is comp + numComps * cell, so the dense index is the GID itself.
+__global__ void k_scatter_grid(const double* __restrict__ x, int stride, const int64_t* __restrict__ gids, int64_t n,
+                               int64_t lo, int64_t hi, double* __restrict__ outRe, double* __restrict__ outIm, int* err) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t g = gids[i];
+    if (g < lo || g >= hi) { *err = 1; continue; }
+    outRe[g - lo] = x[i * stride];
+    if (stride == 2) outIm[g - lo] = x[i * 2 + 1];
+  }
+}
+
 extern "C" {
 
 int mxg_mv_fill(mxg_mv* mv, const double alpha[2]) {
@@ -638,6 +650,40 @@ int mxg_mv_times_mat_add_mv(const double alpha[2], const mxg_mv* A, const double
   MXG_REQUIRE(!overlaps(A, Y), "mxg_mv_times_mat_add_mv: A and Y must not share columns");
   MXG_CUDA(cudaSetDevice(A->map->ctx->device));
   return A->isComplex ? timesMatImpl<zd>(alpha, A, B, ldb, beta, Y) : timesMatImpl<double>(alpha, A, B, ldb, beta, Y);
+}
+
+int mxg_mv_to_grid(const mxg_mv* mv, int col, int64_t gid_lo, int64_t gid_hi, double* out_real, double* out_imag) {
+  MXG_REQUIRE(mv && out_real, "mxg_mv_to_grid: NULL argument");
+  MXG_REQUIRE(col >= 0 && col < mv->ncols, "mxg_mv_to_grid: column %d out of range (%d columns)", col, mv->ncols);
+  MXG_REQUIRE(gid_hi >= gid_lo, "mxg_mv_to_grid: empty or reversed GID range");
+  MXG_REQUIRE(!mv->isComplex || out_imag, "mxg_mv_to_grid: complex field needs out_imag");
+  mxg_ctx* ctx = mv->map->ctx;
+  MXG_CUDA(cudaSetDevice(ctx->device));
+  const int64_t len = gid_hi - gid_lo, n = mv->ld;
+  if (len == 0) { MXG_REQUIRE(n == 0, "mxg_mv_to_grid: owned DOFs outside the GID range"); return MXG_OK; }
+  const int parts = mv->isComplex ? 2 : 1;
+  double* dOut = nullptr;
+  int* dErr = nullptr;
+  MXG_CUDA(cudaMalloc(&dOut, size_t(len) * parts * sizeof(double) + sizeof(int)));
+  dErr = reinterpret_cast<int*>(dOut + size_t(len) * parts);
+  cudaError_t e = cudaMemsetAsync(dOut, 0, size_t(len) * parts * sizeof(double) + sizeof(int), ctx->stream);
+  if (e == cudaSuccess && n > 0) {
+    const int blocks = int(std::min<int64_t>((n + 255) / 256, 148 * 8));
+    k_scatter_grid<<<blocks, 256, 0, ctx->stream>>>(static_cast<const double*>(mv->col[col]), parts, mv->map->dGids, n, gid_lo, gid_hi,
+                                                    dOut, dOut + len, dErr);
+    ++ctx->launches;
+    e = cudaGetLastError();
+  }
+  int hErr = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_real, dOut, size_t(len) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && mv->isComplex)
+    e = cudaMemcpyAsync(out_imag, dOut + len, size_t(len) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&hErr, dErr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dOut);
+  MXG_REQUIRE(e == cudaSuccess, "mxg_mv_to_grid: %s", cudaGetErrorString(e));
+  MXG_REQUIRE(hErr == 0, "mxg_mv_to_grid: owned DOFs outside the GID range [%lld, %lld)", (long long)gid_lo, (long long)gid_hi);
+  return MXG_OK;
 }
 
 }  // extern "C"

@@ -183,3 +183,34 @@ def test_argument_errors_are_reported(mx, ctx):
     e = mx.MxMultiVector(empty, 2)
     e.random(1)
     assert np.all(e.norm2() == 0)
+
+
+@pytest.mark.parametrize("is_complex", [False, True])
+def test_to_grid_matches_mxio_layout(mx, ctx, orc, is_complex):
+    """mxg_mv_to_grid: the dense [x][y][z][comp] node-grid array MxIO::save writes (src/MxIO.cpp:166-221),
+    zeros at DOFs the map masks out; bit-exact scatter by GID."""
+    n = 10
+    sim = orc.pillbox(n)
+    gids = sim.map("bfield")
+    m = mx.MxMap(ctx, sim.num_global("bfield"), gids)
+    x = mx.MxMultiVector(m, 3, is_complex)
+    x.random(5)
+    xh = x.to_host()
+    total = 3 * (n + 1) ** 3
+    for col in (0, 2):
+        want = np.zeros(total, dtype=xh.dtype)
+        want[gids] = xh[:, col]
+        got = x.to_grid(col, 0, total)
+        assert np.array_equal(got, want)
+        arr = got.reshape(n + 1, n + 1, n + 1, 3)
+        assert np.all(arr[0] == 0)                         # the x = 0 plane lies in the metal
+    lo, hi = int(gids.min()), int(gids.max()) + 1          # a sub-range holding every owned DOF works too
+    assert np.array_equal(x.to_grid(1, lo, hi), _dense(gids, xh[:, 1], lo, hi))
+    with pytest.raises(mx.MxError):
+        x.to_grid(0, lo + 5, hi)
+
+
+def _dense(gids, vals, lo, hi):
+    out = np.zeros(hi - lo, dtype=vals.dtype)
+    out[gids - lo] = vals
+    return out
