@@ -32,3 +32,26 @@ def test_shims_on_gpu(tmp_path, mx, ctx):
     exe = _build(tmp_path, mx)
     res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "PASSED" in res.stdout, res.stdout + res.stderr
+
+
+def test_dense_helpers_on_cpu(tmp_path, mx):
+    """mx::dense (Cholesky, Jacobi symEig, generalized / rank-revealing generalized eigenproblem): host logic of the
+    LOBPCG driver, checked without a GPU."""
+    exe = str(tmp_path / "dense_check")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    libdir = os.path.dirname(mx.library_path())
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "dense_check.cpp"), "-o", exe, "-L", libdir, "-lmxgpu",
+                           "-Wl,-rpath," + libdir])
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and "PASSED" in res.stdout, res.stdout + res.stderr
+
+
+def test_public_headers_are_plain_c(tmp_path, mx):
+    exe = str(tmp_path / "abi_is_c")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    libdir = os.path.dirname(mx.library_path())
+    subprocess.check_call([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "abi_is_c.c"), "-o", exe, "-L", libdir, "-lmxgpu", "-lmxsolver",
+                           "-Wl,-rpath," + libdir])
+    assert subprocess.run([exe], timeout=60).returncode == 0
