@@ -170,9 +170,7 @@ struct mxg_crs {
   // 1 / diagonal (0 where the diagonal is 0 or absent); only for square operators whose row
   // and domain maps coincide -- the smoothers of the multigrid cycle use it
   void* dInvDiag = nullptr;
-  // most frequent row patterns, passed to the dictionary kernel in its parameter block (host copy)
-  void* hHot = nullptr;
-  int64_t hotRowsCovered = 0;
+  int ilv = 1;                         // dictionary kernel: thread -> row interleave (1 or 3)
   // captured CUDA graphs of the multi-rank apply (pack -> NCCL exchange || interior rows -> boundary rows),
   // keyed by the operand pointers; replaying one costs a single launch instead of ~10 enqueues
   struct GraphEntry {

@@ -48,18 +48,6 @@ struct __align__(8) PatEntry<zd> {
 
 using Peer = mxg::HaloPeer;
 
-// The most frequent row patterns travel in the kernel parameter block (constant bank): their
-// entries are fetched with LDC instead of L1 loads. ncu showed the dictionary kernel bound by L1
-// data-pipe wavefronts, half of them pattern-table loads; the constant path takes those off L1.
-constexpr int kHotPats = 96;
-template <class T>
-struct HotTable {
-  static constexpr int kEntries = sizeof(T) == 8 ? 960 : 600;
-  PatEntry<T> e[kEntries];
-  uint16_t off[kHotPats + 1];
-  int nHot;
-};
-
 // ---- exact (unfused) accumulation --------------------------------------------------------
 __device__ __forceinline__ void accum(double& acc, double v, double x) { acc = __dadd_rn(acc, __dmul_rn(v, x)); }
 __device__ __forceinline__ void accum(zd& acc, zd v, zd x) {
@@ -122,22 +110,19 @@ struct SellArgs {
 };
 
 template <class T, bool GHOST, int NV>
-__device__ __forceinline__ void dictRow(int64_t row, const DictArgs<T>& D, const HotTable<T>& H, const XSource<T>& X,
+__device__ __forceinline__ void dictRow(int64_t row, const DictArgs<T>& D, const XSource<T>& X,
                                         const ColTable<T>& Y, int nvec, const Epilogue<T>& ep) {
   const int32_t p = D.rowPat[row];
   if (p < 0) return;
-  const bool hot = p < H.nHot;   // pattern entries from the constant bank (opt-in, see buildImpl)
-  int32_t o, oe;
-  if (hot) { o = H.off[p]; oe = H.off[p + 1]; }
-  else { o = __ldg(D.patOff + p); oe = __ldg(D.patOff + p + 1); }
+  const int32_t o = __ldg(D.patOff + p), oe = __ldg(D.patOff + p + 1);
   for (int j0 = 0; j0 < nvec; j0 += NV) {
     T acc[NV];
 #pragma unroll
     for (int jj = 0; jj < NV; ++jj) acc[jj] = zeroOf<T>();
     int32_t q = o;
     for (; q + 1 < oe; q += 2) {
-      const PatEntry<T> e0 = hot ? H.e[q] : D.pat[q];
-      const PatEntry<T> e1 = hot ? H.e[q + 1] : D.pat[q + 1];
+      const PatEntry<T> e0 = D.pat[q];
+      const PatEntry<T> e1 = D.pat[q + 1];
       T x0[NV], x1[NV];
 #pragma unroll
       for (int jj = 0; jj < NV; ++jj) {
@@ -150,7 +135,7 @@ __device__ __forceinline__ void dictRow(int64_t row, const DictArgs<T>& D, const
       for (int jj = 0; jj < NV; ++jj) accum(acc[jj], entryVal(e1), x1[jj]);
     }
     if (q < oe) {
-      const PatEntry<T> e0 = hot ? H.e[q] : D.pat[q];
+      const PatEntry<T> e0 = D.pat[q];
 #pragma unroll
       for (int jj = 0; jj < NV; ++jj) accum(acc[jj], entryVal(e0), loadX<T, GHOST>(X, min(j0 + jj, nvec - 1), row + e0.d));
     }
@@ -208,10 +193,22 @@ __device__ __forceinline__ void sellRow(int64_t i, const SellArgs<T>& S, const X
 
 template <class T, bool GHOST, int NV>
 __global__ void __launch_bounds__(kBlock) k_spmm_dict(int64_t rowBegin, int64_t rowEnd, DictArgs<T> D,
-                                                      const __grid_constant__ HotTable<T> H,
                                                       XSource<T> X, ColTable<T> Y, int nvec, Epilogue<T> ep) {
   const int64_t row = rowBegin + blockIdx.x * int64_t(kBlock) + threadIdx.x;
-  if (row < rowEnd) dictRow<T, GHOST, NV>(row, D, H, X, Y, nvec, ep);
+  if (row < rowEnd) dictRow<T, GHOST, NV>(row, D, X, Y, nvec, ep);
+}
+
+// Same rows, different thread -> row assignment for maps whose DOFs come in component triples (GID = comp + 3 cell,
+// the B/E fields): warp w of a 96-row tile takes rows tile + 3 lane + (w mod 3), i.e. 32 consecutive CELLS of ONE field
+// component. All lanes then share one pattern (one broadcast wavefront per entry instead of ~3) and gather x from one
+// neighbourhood instead of three. Chosen per matrix at build time (mxg_crs::ilv), see buildImpl.
+constexpr int kBlockIlv = 384;   // 4 tiles of 3 warps
+template <class T, bool GHOST, int NV>
+__global__ void __launch_bounds__(kBlockIlv) k_spmm_dict_ilv3(int64_t rowBegin, int64_t rowEnd, DictArgs<T> D,
+                                                              XSource<T> X, ColTable<T> Y, int nvec, Epilogue<T> ep) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = rowBegin + blockIdx.x * int64_t(kBlockIlv) + (warp / 3) * 96 + 3 * lane + (warp % 3);
+  if (row < rowEnd) dictRow<T, GHOST, NV>(row, D, X, Y, nvec, ep);
 }
 
 template <class T, bool GHOST, int NV>
@@ -239,7 +236,6 @@ struct WaitArgs {
 };
 template <class T, bool GHOST, int NV>
 __global__ void __launch_bounds__(kBlock) k_spmm_multi(Segments G, DictArgs<T> D, SellArgs<T> S,
-                                                       const __grid_constant__ HotTable<T> H,
                                                        XSource<T> X, ColTable<T> Y, int nvec, Epilogue<T> ep, WaitArgs W) {
   if (GHOST && W.n > 0) {
     if (threadIdx.x < W.n) {
@@ -259,7 +255,7 @@ __global__ void __launch_bounds__(kBlock) k_spmm_multi(Segments G, DictArgs<T> D
   while (seg < 3 && int(blockIdx.x) >= G.blockStart[seg + 1]) ++seg;
   const int64_t idx = G.begin[seg] + int64_t(int(blockIdx.x) - G.blockStart[seg]) * kBlock + threadIdx.x;
   if (idx >= G.end[seg]) return;
-  if (seg < 2) dictRow<T, GHOST, NV>(idx, D, H, X, Y, nvec, ep);
+  if (seg < 2) dictRow<T, GHOST, NV>(idx, D, X, Y, nvec, ep);
   else sellRow<T, GHOST, NV>(idx, S, X, Y, nvec, ep);
 }
 
@@ -298,10 +294,9 @@ int launchSegments(const mxg_crs* A, const int64_t b[4], const int64_t e[4], con
   if (blocks == 0) return MXG_OK;
   const DictArgs<T> D = dictArgs<T>(A);
   const SellArgs<T> S = sellArgs<T>(A);
-  const HotTable<T>& H = *static_cast<const HotTable<T>*>(A->hHot);
-  if (nvec == 1) k_spmm_multi<T, GHOST, 1><<<blocks, kBlock, 0, st>>>(G, D, S, H, X, Y, nvec, ep, W);
-  else if (nvec == 2) k_spmm_multi<T, GHOST, 2><<<blocks, kBlock, 0, st>>>(G, D, S, H, X, Y, nvec, ep, W);
-  else k_spmm_multi<T, GHOST, 4><<<blocks, kBlock, 0, st>>>(G, D, S, H, X, Y, nvec, ep, W);
+  if (nvec == 1) k_spmm_multi<T, GHOST, 1><<<blocks, kBlock, 0, st>>>(G, D, S, X, Y, nvec, ep, W);
+  else if (nvec == 2) k_spmm_multi<T, GHOST, 2><<<blocks, kBlock, 0, st>>>(G, D, S, X, Y, nvec, ep, W);
+  else k_spmm_multi<T, GHOST, 4><<<blocks, kBlock, 0, st>>>(G, D, S, X, Y, nvec, ep, W);
   LAUNCH_CHECK(ctx);
   return MXG_OK;
 }
@@ -318,12 +313,18 @@ int launchRange(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, int64_t genB
   const bool prof = ctx->profiling;
   if (prof) MXG_CUDA(cudaEventRecord(ctx->prof[1], ctx->stream));
   if (A->dictRows > 0 && rowEnd > rowBegin) {
-    const int64_t blocks = (rowEnd - rowBegin + kBlock - 1) / kBlock;
     const DictArgs<T> D = dictArgs<T>(A);
-    const HotTable<T>& H = *static_cast<const HotTable<T>*>(A->hHot);
-    if (nvec == 1) k_spmm_dict<T, GHOST, 1><<<blocks, kBlock, 0, st>>>(rowBegin, rowEnd, D, H, X, Y, nvec, ep);
-    else if (nvec == 2) k_spmm_dict<T, GHOST, 2><<<blocks, kBlock, 0, st>>>(rowBegin, rowEnd, D, H, X, Y, nvec, ep);
-    else k_spmm_dict<T, GHOST, 4><<<blocks, kBlock, 0, st>>>(rowBegin, rowEnd, D, H, X, Y, nvec, ep);
+    if (A->ilv == 3) {
+      const int64_t blocks = (rowEnd - rowBegin + kBlockIlv - 1) / kBlockIlv;
+      if (nvec == 1) k_spmm_dict_ilv3<T, GHOST, 1><<<blocks, kBlockIlv, 0, st>>>(rowBegin, rowEnd, D, X, Y, nvec, ep);
+      else if (nvec == 2) k_spmm_dict_ilv3<T, GHOST, 2><<<blocks, kBlockIlv, 0, st>>>(rowBegin, rowEnd, D, X, Y, nvec, ep);
+      else k_spmm_dict_ilv3<T, GHOST, 4><<<blocks, kBlockIlv, 0, st>>>(rowBegin, rowEnd, D, X, Y, nvec, ep);
+    } else {
+      const int64_t blocks = (rowEnd - rowBegin + kBlock - 1) / kBlock;
+      if (nvec == 1) k_spmm_dict<T, GHOST, 1><<<blocks, kBlock, 0, st>>>(rowBegin, rowEnd, D, X, Y, nvec, ep);
+      else if (nvec == 2) k_spmm_dict<T, GHOST, 2><<<blocks, kBlock, 0, st>>>(rowBegin, rowEnd, D, X, Y, nvec, ep);
+      else k_spmm_dict<T, GHOST, 4><<<blocks, kBlock, 0, st>>>(rowBegin, rowEnd, D, X, Y, nvec, ep);
+    }
     LAUNCH_CHECK(ctx);
   }
   if (prof) MXG_CUDA(cudaEventRecord(ctx->prof[2], ctx->stream));
@@ -912,21 +913,27 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
   }
   A->numPats = int64_t(patOff.size()) - 1;
   A->patEntries = int64_t(pat.size());
-  {  // hot table: the most frequent patterns, as many as fit
-    auto* H = new HotTable<T>();
-    std::memset(H, 0, sizeof(*H));
-    int nh = 0;
-    while (nh < kHotPats && nh < A->numPats && patOff[nh + 1] <= HotTable<T>::kEntries) ++nh;
-    // Measured on B200 (pillbox-256): 0.351 ms with the constant path vs 0.305 ms without -- a warp
-    // holds ~3 different patterns, and divergent LDC replays cost more than L1 broadcast loads.
-    // The path is therefore opt-in (MXG_SPMV_HOT=1); see profiles/README_r01.md.
-    if (!std::getenv("MXG_SPMV_HOT")) nh = 0;
-    H->nHot = nh;
-    for (int q = 0; q <= nh; ++q) H->off[q] = uint16_t(patOff[q]);
-    for (int q = 0; q < (nh ? patOff[nh] : 0); ++q) H->e[q] = pat[q];
-    A->hHot = H;
-    A->hotRowsCovered = 0;
-    for (int64_t r = 0; r < nRows; ++r) A->hotRowsCovered += (rowPat[r] >= 0 && rowPat[r] < nh);
+  // (A constant-bank copy of the most frequent patterns was tried and removed: 0.351 ms vs 0.305 ms per apply on
+  // pillbox-256 -- a warp holds ~3 different patterns and divergent LDC replays cost more than L1 broadcast loads;
+  // the 16 KB parameter block also lengthened every launch. profiles/README_r01.md.)
+
+  // ---- thread -> row assignment of the dictionary kernel: stride-3 interleave when rows three apart share their
+  // pattern (component triples) far more often than adjacent rows do. MXG_SPMV_ILV = 1 / 3 forces, "auto" decides
+  // from the patterns; unset = plain assignment (the interleave is not yet the measured default).
+  {
+    A->ilv = 1;
+    const char* env = std::getenv("MXG_SPMV_ILV");
+    if (env && std::string(env) == "3") A->ilv = 3;
+    else if (env && std::string(env) == "auto") {
+      int64_t same1 = 0, same3 = 0, cnt = 0;
+      for (int64_t r = 0; r + 3 < nRows; ++r) {
+        if (rowPat[r] < 0) continue;
+        ++cnt;
+        same1 += rowPat[r + 1] == rowPat[r];
+        same3 += rowPat[r + 3] == rowPat[r];
+      }
+      if (cnt > 0 && same3 * 10 >= cnt * 8 && same1 * 10 <= cnt * 5) A->ilv = 3;
+    }
   }
 
   // ---- general rows in sliced ELL; the three row classes (leading boundary, interior,
@@ -1067,7 +1074,6 @@ int mxg_crs_destroy(mxg_crs* A) {
   void* ptrs[] = {A->dRowPat, A->dPatOff, A->dPat, A->dGenRow, A->dGenLen, A->dSlicePtr, A->dCol, A->dVal, A->dSendIdx, A->dSendBuf, A->dGhost, A->dInvDiag};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  if (A->hHot) { if (A->isComplex) delete static_cast<HotTable<zd>*>(A->hHot); else delete static_cast<HotTable<double>*>(A->hHot); }
   mxg_map_destroy(A->rowMap);
   mxg_map_destroy(A->domMap);
   delete A;
