@@ -143,7 +143,8 @@ def run_reference(args):
         "impl": "reference", "metric": "curlcurl_spmv_crs_equiv_gbs", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s-%d curlCurl SpMV" % (args.workload, args.size), "rows": op.nrows, "nnz": op.nnz, "nvec": b},
+        "config": {"workload": "%s-%d curlCurl SpMV (Dey-Mittra, %d rows, %d nnz)" % (args.workload, args.size, op.nrows, op.nnz),
+                   "nvec": b, "layout": "crs (Epetra order)", "partition": "rows over %d host threads" % threads},
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port",
                          "sample": "%d full-operator applies (Epetra-order CSR, OpenMP static rows)" % args.steps},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -214,6 +215,7 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--workload", default="pillbox")
     ap.add_argument("--nvec", type=int, default=1)
+    ap.add_argument("--no-sweep", action="store_true", help="skip the informational 4- and 10-vector block applies")
     ap.add_argument("--layout", default="dict", choices=["dict", "sell"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
@@ -333,6 +335,26 @@ def main():
     if world > 1:
         split = {"interior_ms": acc["dict_ms"], "boundary_ms": acc["sell_ms"], "nccl_ms": acc["pre_ms"], "total_ms": acc["total_ms"]}
 
+    # ---- block applies (b in {1, 4, 10}); informational, same operator and generator ----
+    sweep = None
+    if world == 1 and b == 1 and not args.no_sweep:
+        sweep = {}
+        for nb in (4, 10):
+            xb = mx.MxMultiVector(bmap, nb, is_complex)
+            yb = mx.MxMultiVector(bmap, nb, is_complex)
+            xb.random(12345)
+            for _ in range(3):
+                A.apply(xb, yb)
+            ctx.sync()
+            ctx.event_record(0)
+            for _ in range(30):
+                A.apply(xb, yb)
+            ctx.event_record(1)
+            t_nb = ctx.event_elapsed_ms(0, 1) / 30
+            sweep[str(nb)] = {"ms_per_apply": t_nb, "ms_per_vector": t_nb / nb,
+                              "crs_equiv_gbs": crs_bytes(nnz_g, nrows_g, nb, is_complex) / (t_nb * 1e-3) / 1e9}
+            del xb, yb
+
     # ---- e2e: host buffers through the C ABI (H2D of x, apply, D2H of y every step) ------------
     n_loc = r1 - r0
     dt = np.complex128 if is_complex else np.float64
@@ -423,6 +445,7 @@ def main():
             "clocks": sampler.summary(w0, w1),
             "wall_s_timed": w1 - w0,
             "eigensolve": solve,
+            "block_applies": sweep,
         }
         print(json.dumps(out))
         if world > 1:
