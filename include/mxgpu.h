@@ -159,6 +159,11 @@ int mxg_crs_destroy(mxg_crs* A);
  * On several ranks the ghost entries of x are exchanged with NCCL send/recv, overlapped
  * with the rows that need no ghosts. x and y must not alias. */
 int mxg_crs_apply(const mxg_crs* A, const mxg_mv* x, mxg_mv* y);
+/* Host-buffer form of apply for callers that keep their vectors in host memory (what MxCrsMatrix::apply sees when
+ * the multivectors are still Epetra objects): y_host[i] = A x_host[i], i < count, one column each, local length of the
+ * domain / row map, (re,im) interleaved for complex operators. Uploads, applies and downloads are pipelined over two
+ * device slots; pinned host buffers (mxg_host_alloc) make the copies asynchronous. Returns when every y is complete. */
+int mxg_crs_apply_host_batch(const mxg_crs* A, int count, const double* const* x_host, double* const* y_host);
 /* y = alpha*A*x + beta*y fused into the SpMM epilogue (residuals r = b - A x of the
  * multigrid cycle, MxGeoMultigridPrec.cpp:312-314; shifted operators, MxMagWaveOp.cpp:247-256) */
 int mxg_crs_apply_axpby(const mxg_crs* A, const double alpha[2], const mxg_mv* x, const double beta[2], mxg_mv* y);

@@ -89,6 +89,7 @@ def load_library():
         "mxg_crs_create_opts": (i32, [vp, vp, vp, vp, vp, i32, i32, pvp]),
         "mxg_crs_destroy": (i32, [vp]),
         "mxg_crs_apply": (i32, [vp, vp, vp]),
+        "mxg_crs_apply_host_batch": (i32, [vp, i32, vp, vp]),
         "mxg_crs_apply_axpby": (i32, [vp, dp, vp, dp, vp]),
         "mxg_crs_stats": (i32, [vp, vp]),
         "mxg_mv_get_map": (vp, [vp]),
@@ -455,6 +456,15 @@ class MxCrsMatrix:
 
     def apply(self, x, y):
         _ck(self._L.mxg_crs_apply(self.h, x.h, y.h))
+
+    def apply_host_batch(self, xs, ys):
+        """ys[i] = A xs[i] for host arrays (one column each; pinned arrays make the copies asynchronous); uploads,
+        applies and downloads are pipelined inside the library."""
+        n = len(xs)
+        assert len(ys) == n
+        xp = (C.c_void_p * n)(*[a.ctypes.data for a in xs])
+        yp = (C.c_void_p * n)(*[a.ctypes.data for a in ys])
+        _ck(self._L.mxg_crs_apply_host_batch(self.h, n, xp, yp))
 
     def apply_axpby(self, alpha, x, beta, y):
         _ck(self._L.mxg_crs_apply_axpby(self.h, _scalar(alpha), x.h, _scalar(beta), y.h))

@@ -1105,6 +1105,65 @@ int mxg_crs_apply(const mxg_crs* A, const mxg_mv* x, mxg_mv* y) {
   return applyImpl<double>(A, x, y, ep);
 }
 
+// Host-buffer batch apply: y_host[i] = A x_host[i]. Two device slots and two copy streams, so the upload of item
+// i+1 and the download of item i-1 run while item i is applied (PCIe is full duplex); every item still crosses the
+// bus in both directions. Returns when all results are in host memory.
+int mxg_crs_apply_host_batch(const mxg_crs* A, int count, const double* const* x_host, double* const* y_host) {
+  MXG_REQUIRE(A && (count == 0 || (x_host && y_host)), "mxg_crs_apply_host_batch: NULL argument");
+  MXG_REQUIRE(count >= 0, "mxg_crs_apply_host_batch: negative count");
+  if (count == 0) return MXG_OK;
+  for (int i = 0; i < count; ++i) MXG_REQUIRE(x_host[i] && y_host[i], "mxg_crs_apply_host_batch: NULL buffer %d", i);
+  mxg_ctx* ctx = A->ctx;
+  MXG_CUDA(cudaSetDevice(ctx->device));
+  const size_t esz = A->isComplex ? 16 : 8;
+  mxg_mv *xs[2] = {nullptr, nullptr}, *ys[2] = {nullptr, nullptr};
+  cudaStream_t sUp = nullptr, sDown = nullptr;
+  cudaEvent_t evUp[2] = {nullptr, nullptr}, evApply[2] = {nullptr, nullptr}, evDown[2] = {nullptr, nullptr};
+  int rc = MXG_OK;
+  cudaError_t e = cudaSuccess;
+  auto ok = [&]() { return rc == MXG_OK && e == cudaSuccess; };
+  for (int s = 0; s < 2 && ok(); ++s) {
+    rc = mxg_mv_create(A->domMap, 1, A->isComplex, &xs[s]);
+    if (rc == MXG_OK) rc = mxg_mv_create(A->rowMap, 1, A->isComplex, &ys[s]);
+    if (ok()) e = cudaEventCreateWithFlags(&evUp[s], cudaEventDisableTiming);
+    if (ok()) e = cudaEventCreateWithFlags(&evApply[s], cudaEventDisableTiming);
+    if (ok()) e = cudaEventCreateWithFlags(&evDown[s], cudaEventDisableTiming);
+  }
+  if (ok()) e = cudaStreamCreateWithFlags(&sUp, cudaStreamNonBlocking);
+  if (ok()) e = cudaStreamCreateWithFlags(&sDown, cudaStreamNonBlocking);
+  for (int i = 0; i < count && ok(); ++i) {
+    const int s = i & 1;
+    // x slot is free once the apply of item i-2 has consumed it
+    if (i >= 2) e = cudaStreamWaitEvent(sUp, evApply[s], 0);
+    if (ok() && xs[s]->ld) e = cudaMemcpyAsync(xs[s]->col[0], x_host[i], size_t(xs[s]->ld) * esz, cudaMemcpyHostToDevice, sUp);
+    if (ok()) e = cudaEventRecord(evUp[s], sUp);
+    if (ok()) e = cudaStreamWaitEvent(ctx->stream, evUp[s], 0);
+    // y slot is free once item i-2 has been downloaded
+    if (ok() && i >= 2) e = cudaStreamWaitEvent(ctx->stream, evDown[s], 0);
+    if (ok()) rc = mxg_crs_apply(A, xs[s], ys[s]);
+    if (ok()) e = cudaEventRecord(evApply[s], ctx->stream);
+    if (ok()) e = cudaStreamWaitEvent(sDown, evApply[s], 0);
+    if (ok() && ys[s]->ld) e = cudaMemcpyAsync(y_host[i], ys[s]->col[0], size_t(ys[s]->ld) * esz, cudaMemcpyDeviceToHost, sDown);
+    if (ok()) e = cudaEventRecord(evDown[s], sDown);
+  }
+  // drain everything before the slots are released, also on the error path
+  if (sUp) cudaStreamSynchronize(sUp);
+  cudaStreamSynchronize(ctx->stream);
+  if (sDown) { cudaError_t e2 = cudaStreamSynchronize(sDown); if (e == cudaSuccess) e = e2; }
+  for (int s = 0; s < 2; ++s) {
+    if (evUp[s]) cudaEventDestroy(evUp[s]);
+    if (evApply[s]) cudaEventDestroy(evApply[s]);
+    if (evDown[s]) cudaEventDestroy(evDown[s]);
+    if (xs[s]) mxg_mv_destroy(xs[s]);
+    if (ys[s]) mxg_mv_destroy(ys[s]);
+  }
+  if (sUp) cudaStreamDestroy(sUp);
+  if (sDown) cudaStreamDestroy(sDown);
+  if (rc != MXG_OK) return rc;
+  MXG_REQUIRE(e == cudaSuccess, "mxg_crs_apply_host_batch: %s", cudaGetErrorString(e));
+  return MXG_OK;
+}
+
 int mxg_crs_apply_axpby(const mxg_crs* A, const double alpha[2], const mxg_mv* x, const double beta[2], mxg_mv* y) {
   int rc = checkApply("mxg_crs_apply_axpby", A, x, y);
   if (rc) return rc;

@@ -7,7 +7,7 @@ timeout 420 python -m pytest tests/test_gpu_spmv.py tests/test_gpu_crabcav.py te
 echo "t1 rc=$? $(( $(date +%s) - t0 ))s"; tail -3 gpurun_out/t1.log
 timeout 420 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 echo "bench default rc=$? $(( $(date +%s) - t0 ))s"
-MXG_SPMV_ILV=auto timeout 420 python bench.py --no-cpu > gpurun_out/bench_ilv.json 2> gpurun_out/bench_ilv.err
+MXG_SPMV_ILV=auto timeout 300 python bench.py --no-cpu --no-solve > gpurun_out/bench_ilv.json 2> gpurun_out/bench_ilv.err
 echo "bench ilv rc=$? $(( $(date +%s) - t0 ))s"
 timeout 420 python -m pytest tests/test_gpu_solver.py tests/test_gpu_dielectric.py tests/test_gpu_multi.py tests/test_cpp_shims.py -m gpu -q > gpurun_out/t2.log 2>&1
 echo "t2 rc=$? $(( $(date +%s) - t0 ))s"; tail -3 gpurun_out/t2.log
