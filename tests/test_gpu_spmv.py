@@ -139,10 +139,10 @@ def test_full_size_properties_vacuum(mx, ctx, orc):
     assert az.norm2().max() <= 1e-12 * ay.norm2().max()
 
 
-@pytest.mark.parametrize("mode", ["3", "auto"])
+@pytest.mark.parametrize("mode", ["1", "3", "auto"])
 @pytest.mark.parametrize("name,nvec", [("curlCurl", 1), ("curlCurl", 3), ("vecLapl", 6), ("scaLapl", 2), ("curlE", 1)])
 def test_component_interleaved_dictionary_kernel_bit_exact(mx, ctx, orc, monkeypatch, mode, name, nvec):
-    """MXG_SPMV_ILV: the dictionary kernel with warps covering 32 cells of one field component (rows r, r+3, r+6, ...).
+    """MXG_SPMV_ILV (default auto): the dictionary kernel with warps covering 32 cells of one field component (rows r, r+3, ...).
     A different thread -> row assignment only; results stay bit-identical for every operator, also those whose rows
     do not come in triples (scaLapl) and row counts that are not multiples of the 96-row tile."""
     monkeypatch.setenv("MXG_SPMV_ILV", mode)
