@@ -24,6 +24,7 @@
 #include <unordered_map>
 
 #include "mxg_internal.h"
+#include "mxg_ilv_model.h"
 
 using namespace mxg;
 
@@ -917,23 +918,19 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
   // pillbox-256 -- a warp holds ~3 different patterns and divergent LDC replays cost more than L1 broadcast loads;
   // the 16 KB parameter block also lengthened every launch. profiles/README_r01.md.)
 
-  // ---- thread -> row assignment of the dictionary kernel: stride-3 interleave when rows three apart share their
-  // pattern (component triples: GID = comp + 3 cell) far more often than adjacent rows do. Measured on pillbox-256
-  // curl-curl: 0.262 ms vs 0.297 ms per apply (profiles/README_r01.md). MXG_SPMV_ILV = 1 / 3 forces either.
+  // ---- thread -> row assignment of the dictionary kernel: plain, or stride-3 component interleave. Chosen by a
+  // line-count model over sampled interior tiles (mxg_ilv_model.h, with the B200 measurements that calibrate it).
+  // MXG_SPMV_ILV = 1 / 3 forces either.
   {
     const char* env = std::getenv("MXG_SPMV_ILV");
     const std::string mode = env ? env : "auto";
     A->ilv = 1;
     if (mode == "3") A->ilv = 3;
-    else if (mode != "1") {
-      int64_t same1 = 0, same3 = 0, cnt = 0;
-      for (int64_t r = 0; r + 3 < nRows; ++r) {
-        if (rowPat[r] < 0) continue;
-        ++cnt;
-        same1 += rowPat[r + 1] == rowPat[r];
-        same3 += rowPat[r + 3] == rowPat[r];
-      }
-      if (cnt > 0 && same3 * 10 >= cnt * 8 && same1 * 10 <= cnt * 5) A->ilv = 3;
+    else if (mode != "1" && A->dictRows > 0) {
+      const PatEntry<T>* pe = pat.data();
+      const mxg::IlvCost cost = mxg::ilvCostModel(rowPat.data(), patOff.data(), [pe](int32_t q) { return pe[q].d; }, A->intBegin,
+                                                  A->intEnd, int(sizeof(T)), int(sizeof(PatEntry<T>)));
+      if (mxg::ilvWins(cost)) A->ilv = 3;
     }
   }
 
