@@ -398,6 +398,32 @@ def dsphmsph(n, eps=10.0, a=0.37, b=0.49, size=1.0, origin=-0.5):
     return Sim(n, origin=(origin,) * 3, size=(size,) * 3, pec=metal, dielectrics=[(diel, e)])
 
 
+def oct_lower_bcs(pol, l, m, phase="re"):
+    """example/dsphmsph.py:436-493 -- boundary conditions on the x = 0, y = 0, z = 0 symmetry planes that select the
+    spherical multipole (pol 'TM' | 'TE', degree l, order m, phase 're' | 'im') when only one octant is simulated."""
+    res = [PEC if m % 2 else PMC, PMC, PEC if (l - m) % 2 else PMC]
+    flip = {PEC: PMC, PMC: PEC}
+    if phase == "im":
+        res[0], res[1] = flip[res[0]], flip[res[1]]
+    elif phase != "re":
+        raise ValueError("phase must be 're' or 'im'")
+    if pol == "TE":
+        res = [flip[b] for b in res]
+    elif pol != "TM":
+        raise ValueError("pol must be 'TM' or 'TE'")
+    return tuple(res)
+
+
+def dsphmsph_octant(n, lower, eps=10.0, a=0.37, b=0.49, size=0.5):
+    """Config C3 as the reference runs it (example/run.py:14-29,169-179): the octant [0, 0.5]^3, PEC upper boundaries,
+    PEC/PMC symmetry planes `lower` (see oct_lower_bcs), dielectric sphere inside a PEC sphere, both centred on the
+    origin corner."""
+    diel = Shape.sphere(a, (0, 0, 0))
+    metal = Shape.sphere(b, (0, 0, 0))
+    e = np.eye(3) * eps if np.isscalar(eps) else np.asarray(eps)
+    return Sim(n, origin=(0.0,) * 3, size=(size,) * 3, lower=tuple(lower), upper=(PEC,) * 3, pec=metal, dielectrics=[(diel, e)])
+
+
 # eps diag [10.225, 10.225, 9.95], off-diag [yz, xz, xy] = [0.6736.., -0.6736.., -0.825] (MxProblem.cpp:501-506)
 _S = 0.67360967926537398
 SAPPHIRE = np.array([[10.225, -0.825, -_S], [-0.825, 10.225, _S], [-_S, _S, 9.95]])

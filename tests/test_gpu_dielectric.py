@@ -46,3 +46,18 @@ def test_sapphire_crystal_complex_kform_bitwise(mx, ctx, orc, layout):
     for j in range(2):
         yk = K.apply(np.ascontiguousarray(xh[:, j]).view(np.float64)).view(np.complex128)
         assert np.array_equal(yk, got[:, j])
+
+
+@pytest.mark.parametrize("pol", ["TM", "TE"])
+def test_c3_octant_with_symmetry_planes_bit_exact(mx, ctx, orc, pol):
+    """Config C3 as the reference runs it: one octant, PEC/PMC symmetry planes per multipole family
+    (example/run.py:169-179, example/dsphmsph.py:436-493). The mirror-boundary rows make the operators non-symmetric;
+    parity is the bit-exact apply."""
+    sim = orc.dsphmsph_octant(12, orc.oct_lower_bcs(pol, 1, 0))
+    for name in ("curlCurl", "vecLapl"):
+        A, op, rmap, _ = gpu_matrix(mx, ctx, sim, name)
+        x = mx.MxMultiVector(rmap, 3)
+        y = mx.MxMultiVector(rmap, 3)
+        x.random(11)
+        A.apply(x, y)
+        assert np.array_equal(op.apply(x.to_host()), y.to_host()), (pol, name)
