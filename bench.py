@@ -441,7 +441,8 @@ def main():
                 tr = json.load(f).get("%s-%d-%s-%d" % (args.workload, args.size, args.layout, b))
             if tr and world == 1:
                 roof["traffic"] = tr["dram_bytes"]
-                roof["traffic_source"] = "profiles/r01_traffic.json (%s)" % tr["kernel"]
+                roof["traffic_source"] = ("profiles/r01_traffic.json (%s; ncu capture of the plain row assignment -- the "
+                                          "interleaved kernel streams the same arrays)" % tr["kernel"])
         except Exception:
             pass
         out = {
