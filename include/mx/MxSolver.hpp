@@ -240,14 +240,16 @@ struct MxSolverResult {
 };
 
 // Real symmetric generalized problem A x = theta M x (M diagonal / SPD, may be null = identity),
-// optional preconditioner T ~ A^-1.
-class MxSolver {
+// optional preconditioner T ~ A^-1. Written against the MultiVec / Operator surface only, so the multivector type is
+// a template parameter: MxSolver = MxSolverT<MxAnasaziMV<double>> is the GPU instantiation; tests/cpp/solver_host_check.cpp
+// runs the same driver on a plain host multivector (no GPU) to cover its logic in the CPU suite.
+template <class MV>
+class MxSolverT {
   typedef double S;
-  typedef MxAnasaziMV<S> MV;
   typedef mx::SerialDenseMatrix<int, S> Dense;
 
  public:
-  MxSolver(const mx::Operator<S>* A, const mx::Operator<S>* M, const mx::Operator<S>* prec, MxSolverParams p)
+  MxSolverT(const mx::Operator<S>* A, const mx::Operator<S>* M, const mx::Operator<S>* prec, MxSolverParams p)
       : A_(A), M_(M), T_(prec), p_(p) {
     if (p_.blockSize <= 0) p_.blockSize = p_.nev + std::max(4, p_.nev / 2);
     if (p_.blockSize < p_.nev) p_.blockSize = p_.nev;
@@ -260,7 +262,7 @@ class MxSolver {
     const int m = p_.blockSize;
     if (X.GetNumberVecs() != m) throw std::runtime_error("MxSolver::solve: X must have blockSize columns");
     MxSolverResult res;
-    std::shared_ptr<MxMap> map = X.getMap();
+    auto map = X.getMap();
     // S = [X | W | P] and its images under A and M live in three 3m-column allocations; views pick blocks
     MV Sb(map, 3 * m), ASb(map, 3 * m), MSb(map, 3 * m), tmp(map, 2 * m);
     // second set: the Rayleigh-Ritz update writes X_new / P_new straight into it and the sets swap roles (no copy-back)
@@ -530,6 +532,7 @@ class MxSolver {
   const mx::Operator<S>* T_;
   MxSolverParams p_;
 };
+typedef MxSolverT<MxAnasaziMV<double>> MxSolver;
 
 // ---- MxMagWaveOp (src/MxMagWaveOp.{h,cpp}): the shift-invert operator the reference hands to Anasazi ------
 //   Apply:  y = P (L - sigma M)^-1 M x            (MxMagWaveOp.cpp:825-943)

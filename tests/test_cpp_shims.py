@@ -55,3 +55,17 @@ def test_public_headers_are_plain_c(tmp_path, mx):
                            os.path.join(ROOT, "tests", "cpp", "abi_is_c.c"), "-o", exe, "-L", libdir, "-lmxgpu", "-lmxsolver",
                            "-Wl,-rpath," + libdir])
     assert subprocess.run([exe], timeout=60).returncode == 0
+
+
+def test_solver_driver_on_host_multivector(tmp_path, mx):
+    """MxSolverT (the LOBPCG driver behind MxSolver) instantiated on a plain host multivector (tests/cpp/host_mv.hpp):
+    eigenvalues of Dirichlet Laplacians against the analytic spectrum, degenerate eigenvalues, a generalized problem
+    with a preconditioner, rejection of rank-deficient start blocks. Same code as the GPU instantiation."""
+    exe = str(tmp_path / "solver_host_check")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    libdir = os.path.dirname(mx.library_path())
+    subprocess.check_call([cxx, "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "cpp"),
+                           os.path.join(ROOT, "tests", "cpp", "solver_host_check.cpp"), "-o", exe, "-L", libdir, "-lmxgpu",
+                           "-Wl,-rpath," + libdir])
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "PASSED" in res.stdout, res.stdout + res.stderr
