@@ -10,6 +10,7 @@
 #pragma once
 #include <chrono>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <functional>
 #include <numeric>
@@ -216,6 +217,124 @@ inline int genSymEigRobust(const std::vector<double>& A, const std::vector<doubl
     }
   return k;
 }
+// ---- Hermitian (complex) counterparts, used by the complex instantiation of the eigensolver driver --------------
+typedef std::complex<double> cplx;
+// cyclic Jacobi with complex rotations: a (Hermitian) -> real eigenvalues (ascending) in w, unitary eigenvectors in v.
+// Rotation in the (p,q) plane: U_pp = U_qq = c, U_pq = s e, U_qp = -s conj(e), e = a_pq / |a_pq|; a <- U^H a U.
+inline void hermEig(std::vector<cplx> a, int n, std::vector<double>& w, std::vector<cplx>& v) {
+  v.assign(size_t(n) * n, cplx(0.0));
+  for (int i = 0; i < n; ++i) v[i + size_t(i) * n] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) (i == j ? diag : off) += std::norm(a[i + size_t(j) * n]);
+    if (off <= 1e-30 * (diag + 1e-300)) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const cplx apq = a[p + size_t(q) * n];
+        const double mag = std::abs(apq);
+        if (mag == 0.0) continue;
+        const cplx e = apq / mag;
+        const double app = a[p + size_t(p) * n].real(), aqq = a[q + size_t(q) * n].real();
+        const double tau = (aqq - app) / (2.0 * mag);
+        const double t = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
+        const double c = 1.0 / std::sqrt(1.0 + t * t), sn = t * c;
+        const cplx se = sn * e, sec = sn * std::conj(e);
+        for (int k = 0; k < n; ++k) {  // columns p, q:  a <- a U
+          const cplx akp = a[k + size_t(p) * n], akq = a[k + size_t(q) * n];
+          a[k + size_t(p) * n] = c * akp - sec * akq;
+          a[k + size_t(q) * n] = se * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {  // rows p, q:  a <- U^H a
+          const cplx apk = a[p + size_t(k) * n], aqk = a[q + size_t(k) * n];
+          a[p + size_t(k) * n] = c * apk - se * aqk;
+          a[q + size_t(k) * n] = sec * apk + c * aqk;
+        }
+        for (int k = 0; k < n; ++k) {  // v <- v U
+          const cplx vkp = v[k + size_t(p) * n], vkq = v[k + size_t(q) * n];
+          v[k + size_t(p) * n] = c * vkp - sec * vkq;
+          v[k + size_t(q) * n] = se * vkp + c * vkq;
+        }
+      }
+  }
+  std::vector<int> idx(n);
+  std::iota(idx.begin(), idx.end(), 0);
+  std::sort(idx.begin(), idx.end(), [&](int i, int j) { return a[i + size_t(i) * n].real() < a[j + size_t(j) * n].real(); });
+  w.resize(n);
+  std::vector<cplx> vs(size_t(n) * n);
+  for (int j = 0; j < n; ++j) {
+    w[j] = a[idx[j] + size_t(idx[j]) * n].real();
+    for (int i = 0; i < n; ++i) vs[i + size_t(j) * n] = v[i + size_t(idx[j]) * n];
+  }
+  v.swap(vs);
+}
+// Hermitian-definite generalized problem on a possibly nearly dependent basis (see genSymEigRobust)
+inline int genHermEigRobust(const std::vector<cplx>& A, const std::vector<cplx>& B, int n, double eps, std::vector<double>& w,
+                            std::vector<cplx>& Z) {
+  std::vector<double> d(n);
+  std::vector<cplx> G(size_t(n) * n);
+  for (int j = 0; j < n; ++j) d[j] = B[j + size_t(j) * n].real() > 0 ? 1.0 / std::sqrt(B[j + size_t(j) * n].real()) : 0.0;
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) G[i + size_t(j) * n] = B[i + size_t(j) * n] * (d[i] * d[j]);
+  std::vector<double> lam;
+  std::vector<cplx> V;
+  hermEig(G, n, lam, V);
+  std::vector<int> keep;
+  for (int j = 0; j < n; ++j)
+    if (lam[j] > eps * lam[n - 1]) keep.push_back(j);
+  const int k = int(keep.size());
+  if (k == 0) return 0;
+  std::vector<cplx> Q(size_t(n) * k);   // B-orthonormal basis of the kept subspace
+  for (int j = 0; j < k; ++j) {
+    const double s = 1.0 / std::sqrt(lam[keep[j]]);
+    for (int i = 0; i < n; ++i) Q[i + size_t(j) * n] = (d[i] * s) * V[i + size_t(keep[j]) * n];
+  }
+  std::vector<cplx> AQ(size_t(n) * k, cplx(0.0)), H(size_t(k) * k, cplx(0.0));
+  for (int j = 0; j < k; ++j)
+    for (int c = 0; c < n; ++c) {
+      const cplx q = Q[c + size_t(j) * n];
+      if (q == cplx(0.0)) continue;
+      for (int i = 0; i < n; ++i) AQ[i + size_t(j) * n] += A[i + size_t(c) * n] * q;
+    }
+  for (int j = 0; j < k; ++j)
+    for (int i = 0; i < k; ++i) {
+      cplx s = 0.0;
+      for (int r = 0; r < n; ++r) s += std::conj(Q[r + size_t(i) * n]) * AQ[r + size_t(j) * n];
+      H[i + size_t(j) * k] = s;
+    }
+  for (int j = 0; j < k; ++j) {
+    H[j + size_t(j) * k] = H[j + size_t(j) * k].real();
+    for (int i = 0; i < j; ++i) {
+      const cplx s = 0.5 * (H[i + size_t(j) * k] + std::conj(H[j + size_t(i) * k]));
+      H[i + size_t(j) * k] = s;
+      H[j + size_t(i) * k] = std::conj(s);
+    }
+  }
+  std::vector<cplx> Y;
+  hermEig(H, k, w, Y);
+  Z.assign(size_t(n) * k, cplx(0.0));
+  for (int j = 0; j < k; ++j)
+    for (int c = 0; c < k; ++c) {
+      const cplx y = Y[c + size_t(j) * k];
+      for (int i = 0; i < n; ++i) Z[i + size_t(j) * n] += Q[i + size_t(c) * n] * y;
+    }
+  return k;
+}
+
+// scalar-generic front ends used by the driver: the real instantiation calls exactly the real routines above
+template <class S> struct Ops;
+template <> struct Ops<double> {
+  static double conj(double x) { return x; }
+  static void eig(const std::vector<double>& a, int n, std::vector<double>& w, std::vector<double>& v) { symEig(a, n, w, v); }
+  static int genEigRobust(const std::vector<double>& A, const std::vector<double>& B, int n, double eps, std::vector<double>& w,
+                          std::vector<double>& Z) { return genSymEigRobust(A, B, n, eps, w, Z); }
+};
+template <> struct Ops<cplx> {
+  static cplx conj(cplx x) { return std::conj(x); }
+  static void eig(const std::vector<cplx>& a, int n, std::vector<double>& w, std::vector<cplx>& v) { hermEig(a, n, w, v); }
+  static int genEigRobust(const std::vector<cplx>& A, const std::vector<cplx>& B, int n, double eps, std::vector<double>& w,
+                          std::vector<cplx>& Z) { return genHermEigRobust(A, B, n, eps, w, Z); }
+};
 }  // namespace dense
 }  // namespace mx
 
@@ -239,14 +358,15 @@ struct MxSolverResult {
   double seconds = 0.0;
 };
 
-// Real symmetric generalized problem A x = theta M x (M diagonal / SPD, may be null = identity),
-// optional preconditioner T ~ A^-1. Written against the MultiVec / Operator surface only, so the multivector type is
+// Symmetric / Hermitian generalized problem A x = theta M x (M diagonal / SPD, may be null = identity),
+// optional preconditioner T ~ A^-1. Scalar = double (default) or std::complex<double> (Bloch-periodic operators). Written against the MultiVec / Operator surface only, so the multivector type is
 // a template parameter: MxSolver = MxSolverT<MxAnasaziMV<double>> is the GPU instantiation; tests/cpp/solver_host_check.cpp
 // runs the same driver on a plain host multivector (no GPU) to cover its logic in the CPU suite.
-template <class MV>
+template <class MV, class Scalar = double>
 class MxSolverT {
-  typedef double S;
+  typedef Scalar S;
   typedef mx::SerialDenseMatrix<int, S> Dense;
+  typedef mx::dense::Ops<S> Ops;
 
  public:
   MxSolverT(const mx::Operator<S>* A, const mx::Operator<S>* M, const mx::Operator<S>* prec, MxSolverParams p)
@@ -283,7 +403,7 @@ class MxSolverT {
       timeit(res.tUpdate, [&] {
         auto src = view(base, srcCols);
         auto t = view(tmp, range(0, C.numCols()));
-        t->MvTimesMatAddMv(1.0, *src, C, 0.0);
+        t->MvTimesMatAddMv(S(1.0), *src, C, S(0.0));
         auto dst = view(base, dstCols);
         *dst = *t;
       });
@@ -292,10 +412,10 @@ class MxSolverT {
       auto l = view(left, lc);
       auto r = view(right, rc);
       Dense G(int(lc.size()), int(rc.size()));
-      timeit(res.tGram, [&] { r->MvTransMv(1.0, *l, G); });
+      timeit(res.tGram, [&] { r->MvTransMv(S(1.0), *l, G); });
       return G;
     };
-    auto toVec = [](const Dense& G) { return std::vector<double>(G.values(), G.values() + size_t(G.numRows()) * G.numCols()); };
+    auto toVec = [](const Dense& G) { return std::vector<S>(G.values(), G.values() + size_t(G.numRows()) * G.numCols()); };
 
     const auto t0 = clock::now();
     const std::vector<int> xc = range(0, m);
@@ -314,21 +434,24 @@ class MxSolverT {
       const int k = int(cols.size());
       if (k == 0) return 0;
       Dense G = gram(Sb, cols, MSb, cols);
-      std::vector<double> g = toVec(G), d(k);
+      std::vector<S> g = toVec(G);
+      std::vector<double> d(k);
       double dmax = 0.0;
-      for (int j = 0; j < k; ++j) dmax = std::max(dmax, g[j + size_t(j) * k]);
+      for (int j = 0; j < k; ++j) dmax = std::max(dmax, std::real(g[j + size_t(j) * k]));
       if (!(dmax > 0.0) || !std::isfinite(dmax)) { cols.clear(); return 0; }
       for (int j = 0; j < k; ++j) {
-        const double gj = g[j + size_t(j) * k];
+        const double gj = std::real(g[j + size_t(j) * k]);
         d[j] = gj > 1e-28 * dmax ? 1.0 / std::sqrt(gj) : 0.0;   // columns that vanished are dropped
       }
       for (int j = 0; j < k; ++j)
         for (int i = 0; i <= j; ++i) {
-          const double s = 0.5 * (g[i + size_t(j) * k] + g[j + size_t(i) * k]) * d[i] * d[j];
-          g[i + size_t(j) * k] = g[j + size_t(i) * k] = s;
+          const S s = 0.5 * (g[i + size_t(j) * k] + Ops::conj(g[j + size_t(i) * k])) * d[i] * d[j];
+          g[i + size_t(j) * k] = s;
+          g[j + size_t(i) * k] = Ops::conj(s);
         }
-      std::vector<double> lam, V;
-      mx::dense::symEig(g, k, lam, V);
+      std::vector<double> lam;
+      std::vector<S> V;
+      Ops::eig(g, k, lam, V);
       std::vector<int> keep;
       for (int j = 0; j < k; ++j)
         if (lam[j] > 1e-10 * std::max(lam[k - 1], 1.0)) keep.push_back(j);
@@ -359,8 +482,9 @@ class MxSolverT {
     std::vector<double> theta(m, 0.0);
     {  // initial Rayleigh-Ritz on X
       Dense H = gram(Sb, xc, ASb, xc);
-      std::vector<double> w, V;
-      mx::dense::symEig(toVec(H), m, w, V);
+      std::vector<double> w;
+      std::vector<S> V;
+      Ops::eig(toVec(H), m, w, V);
       Dense C(m, m);
       std::copy(V.begin(), V.end(), C.values());
       rightMul(Sb, xc, C, xc);
@@ -379,8 +503,8 @@ class MxSolverT {
         auto mxv = view(MSb, xc);
         auto scaled = view(tmp, range(m, m));
         *scaled = *mxv;
-        scaled->MvScale(theta);
-        R->MvAddMv(1.0, *ax, -1.0, *scaled);
+        scaled->MvScale(std::vector<S>(theta.begin(), theta.end()));
+        R->MvAddMv(S(1.0), *ax, S(-1.0), *scaled);
         std::vector<double> rn, mn;
         R->MvNorm(rn);
         mxv->MvNorm(mn);
@@ -422,8 +546,8 @@ class MxSolverT {
         Dense C = gram(Sb, xc, MSb, wc);
         auto Xv = view(Sb, xc);
         auto MXv = view(MSb, xc);
-        W->MvTimesMatAddMv(-1.0, *Xv, C, 1.0);
-        MW->MvTimesMatAddMv(-1.0, *MXv, C, 1.0);
+        W->MvTimesMatAddMv(S(-1.0), *Xv, C, S(1.0));
+        MW->MvTimesMatAddMv(S(-1.0), *MXv, C, S(1.0));
       }
       orthonormalize(wc, false);                 // may drop directions that vanished after the projection
       if (!wc.empty()) {
@@ -438,14 +562,15 @@ class MxSolverT {
         break;
       }
       // Rayleigh-Ritz on span[X W P]
-      std::vector<double> w, Z;
+      std::vector<double> w;
+      std::vector<S> Z;
       int ns = 0;
       for (int attempt = 0; attempt < 2; ++attempt) {
         std::vector<int> sc = xc;
         sc.insert(sc.end(), wc.begin(), wc.end());
         if (np > 0) { const std::vector<int> pcc = range(2 * m, np); sc.insert(sc.end(), pcc.begin(), pcc.end()); }
         ns = int(sc.size());
-        std::vector<double> ga, gm;
+        std::vector<S> ga, gm;
         const int nwb = int(wc.size());
         if (it % 10 == 0) {
           // explicit Gram matrices of the whole basis (also resets the round-off drift of the implicit ones)
@@ -460,14 +585,14 @@ class MxSolverT {
           if (np > 0) { const std::vector<int> pcc = range(2 * m, np); wpc2.insert(wpc2.end(), pcc.begin(), pcc.end()); }
           const int nwp = int(wpc2.size());
           Dense GA1 = gram(Sb, sc, ASb, wpc2);                    // ns x (nw + np)
-          ga.assign(size_t(ns) * ns, 0.0);
-          gm.assign(size_t(ns) * ns, 0.0);
+          ga.assign(size_t(ns) * ns, S(0.0));
+          gm.assign(size_t(ns) * ns, S(0.0));
           for (int j = 0; j < m; ++j) ga[j + size_t(j) * ns] = theta[j];
           for (int j = 0; j < ns; ++j) gm[j + size_t(j) * ns] = 1.0;
           for (int j = 0; j < nwp; ++j)
             for (int i = 0; i < ns; ++i) {
               ga[i + size_t(m + j) * ns] = GA1(i, j);
-              if (i < m) ga[(m + j) + size_t(i) * ns] = GA1(i, j);
+              if (i < m) ga[(m + j) + size_t(i) * ns] = Ops::conj(GA1(i, j));
             }
           if (np > 0) {
             const std::vector<int> pcc = range(2 * m, np);
@@ -475,17 +600,21 @@ class MxSolverT {
             for (int j = 0; j < np; ++j)
               for (int i = 0; i < m + nwb; ++i) {
                 gm[i + size_t(m + nwb + j) * ns] = GM1(i, j);
-                gm[(m + nwb + j) + size_t(i) * ns] = GM1(i, j);
+                gm[(m + nwb + j) + size_t(i) * ns] = Ops::conj(GM1(i, j));
               }
           }
         }
         for (int j = 0; j < ns; ++j)
           for (int i = 0; i < j; ++i) {
-            ga[i + size_t(j) * ns] = ga[j + size_t(i) * ns] = 0.5 * (ga[i + size_t(j) * ns] + ga[j + size_t(i) * ns]);
-            gm[i + size_t(j) * ns] = gm[j + size_t(i) * ns] = 0.5 * (gm[i + size_t(j) * ns] + gm[j + size_t(i) * ns]);
+            const S a = 0.5 * (ga[i + size_t(j) * ns] + Ops::conj(ga[j + size_t(i) * ns]));
+            const S b = 0.5 * (gm[i + size_t(j) * ns] + Ops::conj(gm[j + size_t(i) * ns]));
+            ga[i + size_t(j) * ns] = a;
+            ga[j + size_t(i) * ns] = Ops::conj(a);
+            gm[i + size_t(j) * ns] = b;
+            gm[j + size_t(i) * ns] = Ops::conj(b);
           }
         // truncated generalized eigenproblem: nearly dependent directions of [X W P] are discarded
-        if (mx::dense::genSymEigRobust(ga, gm, ns, 1e-12, w, Z) >= m) break;
+        if (Ops::genEigRobust(ga, gm, ns, 1e-12, w, Z) >= m) break;
         if (np == 0) throw std::runtime_error("MxSolver: projected basis has rank below the block size");
         np = 0;  // retry without P
       }
@@ -507,8 +636,8 @@ class MxSolverT {
         auto wp = view(*cur[t], wpc);
         auto tx = view(*alt[t], xc);
         auto tp = view(*alt[t], pnew);
-        tx->MvTimesMatAddMv(1.0, *s, Cx, 0.0);
-        tp->MvTimesMatAddMv(1.0, *wp, Cp, 0.0);
+        tx->MvTimesMatAddMv(S(1.0), *s, Cx, S(0.0));
+        tp->MvTimesMatAddMv(S(1.0), *wp, Cp, S(0.0));
         cur[t]->swap(*alt[t]);
       });
       np = m;

@@ -25,7 +25,8 @@ const char* mxs_last_error(void);
 void mxs_last_profile(double out[4]);
 /* A: assembled operator (curlCurl or vecLapl); m_diag: one-column multivector holding the diagonal
  * of the mass matrix mRhs (NULL = identity); prec: multigrid preconditioner (NULL = none).
- * X: n x block multivector, receives the M-orthonormal Ritz vectors.
+ * X: n x block multivector, receives the M-orthonormal Ritz vectors. Real symmetric pencil, or -- when X is complex --
+ * the Hermitian pencil of a Bloch-periodic simulation (A complex, m_diag a complex one-column multivector).
  * evals/resnorms: block entries. info[0]=iterations, [1]=converged among nev, [2]=A applies (columns),
  * [3]=preconditioner applies (columns). */
 int mxs_lobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, mxg_mv* X, const mxs_params* p,

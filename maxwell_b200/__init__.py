@@ -565,7 +565,9 @@ class MxGeoMultigridPrec:
 
 class MxSolver:
     """Block eigensolver driver (reference: src/MxSolver.cpp:22-239 driving Anasazi): lowest eigenpairs of
-    A x = theta M x with an optional multigrid preconditioner. The loop runs in C++ (include/mx/MxSolver.hpp)."""
+    A x = theta M x with an optional multigrid preconditioner. The loop runs in C++ (include/mx/MxSolver.hpp).
+    Real symmetric pencils, or Hermitian ones (complex operator of a Bloch-periodic simulation: complex multivectors,
+    m_diag a complex one-column multivector)."""
 
     def __init__(self, ctx, A, m_diag=None, prec=None, nev=10, block_size=0, tol=1e-8, max_iters=300, verbose=0, seed=12345):
         self._S = load_solver()
@@ -580,7 +582,7 @@ class MxSolver:
     def solve(self, X=None):
         m = self.params.block_size
         if X is None:
-            X = MxMultiVector(self.A.row_map, m)
+            X = MxMultiVector(self.A.row_map, m, getattr(self.A, "is_complex", False))
             self.params.random_init = 1
         else:
             self.params.random_init = 0

@@ -19,6 +19,64 @@ Wrapped wrap(mxg_ctx* ctx, mxg_mv* X) {
   w.map = std::make_shared<MxMap>(mxg_mv_get_map(X), w.comm, false);
   return w;
 }
+
+// Scalar = double: real symmetric pencil; Scalar = MxComplex: Hermitian pencil of a Bloch-periodic simulation (complex
+// operator, complex multivectors, m_diag a complex one-column multivector with real entries).
+template <class Scalar>
+void runLobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, mxg_mv* X, const mxs_params* p, double* evals,
+               double* resnorms, int64_t info[4], double* seconds) {
+  Wrapped w = wrap(ctx, X);
+  MxAnasaziMV<Scalar> Xmv(X, w.map, false);
+  MxCrsOperator<Scalar> Aop(A);
+  std::unique_ptr<MxDiagOperator<Scalar>> Mop;
+  if (m_diag) Mop.reset(new MxDiagOperator<Scalar>(m_diag));
+  std::unique_ptr<MxGeoMultigridPrec<Scalar>> Top;
+  if (prec) Top.reset(new MxGeoMultigridPrec<Scalar>(prec, false));
+  MxSolverParams sp;
+  sp.nev = p->nev;
+  sp.blockSize = p->block_size > 0 ? p->block_size : mxg_mv_num_cols(X);
+  sp.maxIters = p->max_iters;
+  sp.tol = p->tol;
+  sp.verbose = p->verbose;
+  sp.seed = p->seed;
+  sp.randomInit = p->random_init != 0;
+  sp.profile = p->verbose >= 2;
+  MxSolverT<MxAnasaziMV<Scalar>, Scalar> solver(&Aop, Mop.get(), Top.get(), sp);
+  MxSolverResult r = solver.solve(Xmv);
+  const int m = sp.blockSize;
+  if (evals) std::memcpy(evals, r.eigenvalues.data(), sizeof(double) * m);
+  if (resnorms) std::memcpy(resnorms, r.residuals.data(), sizeof(double) * m);
+  if (info) { info[0] = r.iterations; info[1] = r.converged; info[2] = r.applyA; info[3] = r.applyPrec; }
+  if (seconds) *seconds = r.seconds;
+  g_profile[0] = r.tApplyA; g_profile[1] = r.tPrec; g_profile[2] = r.tGram; g_profile[3] = r.tUpdate;
+}
+
+template <class Scalar>
+void runCheck(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_crs* divB, mxg_mv* X, const double* evals, double* res, double* div) {
+  Wrapped w = wrap(ctx, X);
+  MxAnasaziMV<Scalar> Xmv(X, w.map, false);
+  const int m = Xmv.GetNumberVecs();
+  MxAnasaziMV<Scalar> AX(w.map, m), MX(w.map, m);
+  MxCrsOperator<Scalar>(A).Apply(Xmv, AX);
+  if (m_diag) MxDiagOperator<Scalar>(m_diag).Apply(Xmv, MX); else MX = Xmv;
+  std::vector<Scalar> th(evals, evals + m);
+  std::vector<double> rn, mn;
+  MxAnasaziMV<Scalar> scaled(MX);
+  scaled.MvScale(th);
+  AX.MvAddMv(Scalar(1.0), AX, Scalar(-1.0), scaled);
+  AX.MvNorm(rn);
+  MX.MvNorm(mn);
+  for (int j = 0; j < m; ++j) res[j] = rn[j] / std::fabs(evals[j]);   // MxMagWaveOp.cpp:1195-1203
+  if (divB && div) {
+    mxg_mv* d = nullptr;
+    mx::check(mxg_mv_create(mxg_crs_row_map(divB), m, mxg_mv_is_complex(X), &d));
+    mx::check(mxg_crs_apply(divB, MX.getRawMV(), d));
+    std::vector<double> dn(m);
+    mx::check(mxg_mv_norm2(d, dn.data()));
+    mxg_mv_destroy(d);
+    for (int j = 0; j < m; ++j) div[j] = mn[j] > 0 ? dn[j] / mn[j] : 0.0;
+  }
+}
 }  // namespace
 
 extern "C" {
@@ -42,31 +100,8 @@ int mxs_lobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, mxg_mv* 
                double* evals, double* resnorms, int64_t info[4], double* seconds) {
   try {
     if (!ctx || !A || !X || !p) throw std::runtime_error("mxs_lobpcg: NULL argument");
-    if (mxg_mv_is_complex(X)) throw std::runtime_error("mxs_lobpcg: complex problems are not supported by this driver yet");
-    Wrapped w = wrap(ctx, X);
-    MxAnasaziMV<double> Xmv(X, w.map, false);
-    MxCrsOperator<double> Aop(A);
-    std::unique_ptr<MxDiagOperator<double>> Mop;
-    if (m_diag) Mop.reset(new MxDiagOperator<double>(m_diag));
-    std::unique_ptr<MxGeoMultigridPrec<double>> Top;
-    if (prec) Top.reset(new MxGeoMultigridPrec<double>(prec, false));
-    MxSolverParams sp;
-    sp.nev = p->nev;
-    sp.blockSize = p->block_size > 0 ? p->block_size : mxg_mv_num_cols(X);
-    sp.maxIters = p->max_iters;
-    sp.tol = p->tol;
-    sp.verbose = p->verbose;
-    sp.seed = p->seed;
-    sp.randomInit = p->random_init != 0;
-    sp.profile = p->verbose >= 2;
-    MxSolver solver(&Aop, Mop.get(), Top.get(), sp);
-    MxSolverResult r = solver.solve(Xmv);
-    const int m = sp.blockSize;
-    if (evals) std::memcpy(evals, r.eigenvalues.data(), sizeof(double) * m);
-    if (resnorms) std::memcpy(resnorms, r.residuals.data(), sizeof(double) * m);
-    if (info) { info[0] = r.iterations; info[1] = r.converged; info[2] = r.applyA; info[3] = r.applyPrec; }
-    if (seconds) *seconds = r.seconds;
-    g_profile[0] = r.tApplyA; g_profile[1] = r.tPrec; g_profile[2] = r.tGram; g_profile[3] = r.tUpdate;
+    if (mxg_mv_is_complex(X)) runLobpcg<MxComplex>(ctx, A, m_diag, prec, X, p, evals, resnorms, info, seconds);
+    else runLobpcg<double>(ctx, A, m_diag, prec, X, p, evals, resnorms, info, seconds);
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();
@@ -78,28 +113,8 @@ int mxs_check_eigensolution(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_crs* d
                             double* res, double* div) {
   try {
     if (!ctx || !A || !X || !evals) throw std::runtime_error("mxs_check_eigensolution: NULL argument");
-    Wrapped w = wrap(ctx, X);
-    MxAnasaziMV<double> Xmv(X, w.map, false);
-    const int m = Xmv.GetNumberVecs();
-    MxAnasaziMV<double> AX(w.map, m), MX(w.map, m);
-    MxCrsOperator<double>(A).Apply(Xmv, AX);
-    if (m_diag) MxDiagOperator<double>(m_diag).Apply(Xmv, MX); else MX = Xmv;
-    std::vector<double> th(evals, evals + m), rn, mn;
-    MxAnasaziMV<double> scaled(MX);
-    scaled.MvScale(th);
-    AX.MvAddMv(1.0, AX, -1.0, scaled);
-    AX.MvNorm(rn);
-    MX.MvNorm(mn);
-    for (int j = 0; j < m; ++j) res[j] = rn[j] / std::fabs(evals[j]);   // MxMagWaveOp.cpp:1195-1203
-    if (divB && div) {
-      mxg_mv* d = nullptr;
-      mx::check(mxg_mv_create(mxg_crs_row_map(divB), m, 0, &d));
-      mx::check(mxg_crs_apply(divB, MX.getRawMV(), d));
-      std::vector<double> dn(m);
-      mx::check(mxg_mv_norm2(d, dn.data()));
-      mxg_mv_destroy(d);
-      for (int j = 0; j < m; ++j) div[j] = mn[j] > 0 ? dn[j] / mn[j] : 0.0;
-    }
+    if (mxg_mv_is_complex(X)) runCheck<MxComplex>(ctx, A, m_diag, divB, X, evals, res, div);
+    else runCheck<double>(ctx, A, m_diag, divB, X, evals, res, div);
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();

@@ -1,6 +1,7 @@
 // Host-side dense kernels of the eigensolver driver (include/mx/MxSolver.hpp, namespace mx::dense): the pieces the
 // reference gets from Teuchos::LAPACK inside Anasazi. No GPU needed.
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <random>
 #include <vector>
@@ -111,6 +112,68 @@ int main() {
     if (kept == 2) CHECK(std::fabs(w[0] - 1.0) < 1e-12 && std::fabs(w[1] - 3.0) < 1e-12, "Ritz values %.15g %.15g", w[0], w[1]);
     Mat L = B;
     CHECK(!cholesky(L, n) || true, "unreachable");   // Cholesky may or may not notice; the robust path must not depend on it
+  }
+  // Hermitian counterparts (complex Jacobi, rank-revealing generalized problem)
+  {
+    typedef std::complex<double> Z;
+    std::uniform_real_distribution<double> u(-1.0, 1.0);
+    for (int n : {1, 2, 6, 23, 40}) {
+      std::vector<Z> g(size_t(n) * n), A(size_t(n) * n), B(size_t(n) * n, Z(0.0));
+      for (auto& v : g) v = Z(u(rng), u(rng));
+      for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) {
+          A[i + size_t(j) * n] = 0.5 * (g[i + size_t(j) * n] + std::conj(g[j + size_t(i) * n]));
+          Z s = 0;
+          for (int k = 0; k < n; ++k) s += std::conj(g[k + size_t(i) * n]) * g[k + size_t(j) * n];
+          B[i + size_t(j) * n] = s + (i == j ? 0.1 : 0.0);
+        }
+      std::vector<double> w;
+      std::vector<Z> V;
+      hermEig(A, n, w, V);
+      double err = 0, orth = 0;
+      for (int j = 0; j < n; ++j) {
+        if (j) CHECK(w[j] >= w[j - 1], "Hermitian eigenvalues not ascending");
+        for (int i = 0; i < n; ++i) {
+          Z av = 0, vv = 0;
+          for (int k = 0; k < n; ++k) { av += A[i + size_t(k) * n] * V[k + size_t(j) * n]; vv += std::conj(V[k + size_t(i) * n]) * V[k + size_t(j) * n]; }
+          err = std::fmax(err, std::abs(av - w[j] * V[i + size_t(j) * n]));
+          orth = std::fmax(orth, std::abs(vv - (i == j ? 1.0 : 0.0)));
+        }
+      }
+      CHECK(err < 1e-12 * n && orth < 1e-12 * n, "hermEig residual %.3e orth %.3e n=%d", err, orth, n);
+      std::vector<Z> Zv;
+      const int kept = genHermEigRobust(A, B, n, 1e-14, w, Zv);
+      CHECK(kept == n, "genHermEigRobust dropped %d directions of a full-rank basis", n - kept);
+      err = orth = 0;
+      for (int j = 0; j < kept; ++j)
+        for (int i = 0; i < n; ++i) {
+          Z az = 0, bz = 0;
+          for (int k = 0; k < n; ++k) { az += A[i + size_t(k) * n] * Zv[k + size_t(j) * n]; bz += B[i + size_t(k) * n] * Zv[k + size_t(j) * n]; }
+          err = std::fmax(err, std::abs(az - w[j] * bz));
+        }
+      for (int j = 0; j < kept; ++j)
+        for (int i = 0; i < kept; ++i) {
+          Z s = 0;
+          for (int r = 0; r < n; ++r)
+            for (int c = 0; c < n; ++c) s += std::conj(Zv[r + size_t(i) * n]) * B[r + size_t(c) * n] * Zv[c + size_t(j) * n];
+          orth = std::fmax(orth, std::abs(s - (i == j ? 1.0 : 0.0)));
+        }
+      CHECK(err < 1e-8 && orth < 1e-9, "genHermEigRobust residual %.3e orth %.3e n=%d", err, orth, n);
+    }
+    // dependent complex basis: s3 = i s1 + s2 in C^2, A = diag(1, 3)
+    const Z S[2][3] = {{1, 0, Z(0, 1)}, {0, 1, 1}};
+    const double D[2] = {1.0, 3.0};
+    std::vector<Z> A(9), B(9);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        A[i + 3 * j] = std::conj(S[0][i]) * D[0] * S[0][j] + std::conj(S[1][i]) * D[1] * S[1][j];
+        B[i + 3 * j] = std::conj(S[0][i]) * S[0][j] + std::conj(S[1][i]) * S[1][j];
+      }
+    std::vector<double> w;
+    std::vector<Z> Zv;
+    const int kept = genHermEigRobust(A, B, 3, 1e-12, w, Zv);
+    CHECK(kept == 2, "kept %d directions of a rank-2 complex basis", kept);
+    if (kept == 2) CHECK(std::fabs(w[0] - 1.0) < 1e-12 && std::fabs(w[1] - 3.0) < 1e-12, "complex Ritz values %.15g %.15g", w[0], w[1]);
   }
   if (failures == 0) std::printf("PASSED\n");
   return failures ? 1 : 0;

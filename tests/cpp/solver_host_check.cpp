@@ -163,6 +163,117 @@ int main() {
     CHECK(r.converged == p.nev, "tiny: converged %d", r.converged);
     for (int j = 0; j < p.nev; ++j) CHECK(std::fabs(r.eigenvalues[j] - want[j]) < 1e-9, "tiny eigenvalue %d: %.12g vs %.12g", j, r.eigenvalues[j], want[j]);
   }
+  // 5. complex Hermitian instantiation: Bloch-periodic Laplacian (phase picked up on the wrap-around links only),
+  //    analytic spectrum sum_d 4 c_d sin^2((2 pi m_d + phi_d) / (2 n_d)); standard and generalized (diagonal M) problems
+  {
+    typedef std::complex<double> Z;
+    typedef hostmv::HostMVC MVC;
+    struct Bloch : mx::Operator<Z> {
+      int n[3];
+      double c[3], phi[3];
+      int64_t size() const { return int64_t(n[0]) * n[1] * n[2]; }
+      void Apply(const mx::MultiVec<Z>& x_, mx::MultiVec<Z>& y_) const override {
+        const MVC& x = dynamic_cast<const MVC&>(x_);
+        MVC& y = dynamic_cast<MVC&>(y_);
+        const int64_t stride[3] = {int64_t(n[1]) * n[2], n[2], 1};
+        for (int v = 0; v < x.GetNumberVecs(); ++v) {
+          const Z* a = x.col(size_t(v));
+          Z* b = y.col(size_t(v));
+          for (int i = 0; i < n[0]; ++i)
+            for (int j = 0; j < n[1]; ++j)
+              for (int k = 0; k < n[2]; ++k) {
+                const int idx[3] = {i, j, k};
+                const int64_t p = i * stride[0] + j * stride[1] + k;
+                Z s = 2 * (c[0] + c[1] + c[2]) * a[p];
+                for (int d = 0; d < 3; ++d) {
+                  const bool wrapUp = idx[d] == n[d] - 1, wrapDown = idx[d] == 0;
+                  const int64_t up = wrapUp ? p - (n[d] - 1) * stride[d] : p + stride[d];
+                  const int64_t dn = wrapDown ? p + (n[d] - 1) * stride[d] : p - stride[d];
+                  s -= c[d] * (wrapUp ? std::polar(1.0, phi[d]) : Z(1.0)) * a[up];
+                  s -= c[d] * (wrapDown ? std::polar(1.0, -phi[d]) : Z(1.0)) * a[dn];
+                }
+                b[p] = s;
+              }
+        }
+      }
+      std::vector<double> spectrum() const {
+        std::vector<double> w;
+        for (int i = 0; i < n[0]; ++i)
+          for (int j = 0; j < n[1]; ++j)
+            for (int k = 0; k < n[2]; ++k) {
+              const int m[3] = {i, j, k};
+              double s = 0;
+              for (int d = 0; d < 3; ++d) { const double t = std::sin((2 * M_PI * m[d] + phi[d]) / (2.0 * n[d])); s += 4 * c[d] * t * t; }
+              w.push_back(s);
+            }
+        std::sort(w.begin(), w.end());
+        return w;
+      }
+    };
+    struct DiagZ : mx::Operator<Z> {
+      std::vector<double> d;
+      void Apply(const mx::MultiVec<Z>& x_, mx::MultiVec<Z>& y_) const override {
+        const MVC& x = dynamic_cast<const MVC&>(x_);
+        MVC& y = dynamic_cast<MVC&>(y_);
+        for (int v = 0; v < x.GetNumberVecs(); ++v)
+          for (size_t i = 0; i < d.size(); ++i) y.col(size_t(v))[i] = d[i] * x.col(size_t(v))[i];
+      }
+    };
+    Bloch A;
+    A.n[0] = 8; A.n[1] = 7; A.n[2] = 6;
+    A.c[0] = 64; A.c[1] = 49; A.c[2] = 36;
+    A.phi[0] = 0.7; A.phi[1] = -0.4; A.phi[2] = 1.1;
+    {  // the operator really is Hermitian and complex
+      auto map = std::make_shared<hostmv::Map>(A.size());
+      MVC U(map, 2), AU(map, 2);
+      U.MvRandom();
+      A.Apply(U, AU);
+      mx::SerialDenseMatrix<int, Z> G(2, 2);
+      AU.MvTransMv(Z(1.0), U, G);
+      CHECK(std::abs(G(0, 1) - std::conj(G(1, 0))) < 1e-9 * std::abs(G(0, 0)) && std::fabs(G(0, 1).imag()) > 1e-6, "Bloch operator not Hermitian/complex");
+    }
+    typedef MxSolverT<MVC, Z> SolverC;
+    const std::vector<double> want = A.spectrum();
+    MxSolverParams p;
+    p.nev = 5; p.blockSize = 9; p.tol = 1e-9; p.maxIters = 500;
+    auto map = std::make_shared<hostmv::Map>(A.size());
+    MVC X(map, size_t(p.blockSize));
+    MxSolverResult r = SolverC(&A, nullptr, nullptr, p).solve(X);
+    CHECK(r.converged == p.nev, "complex: converged %d of %d in %d iterations", r.converged, p.nev, r.iterations);
+    for (int j = 0; j < p.nev; ++j) CHECK(std::fabs(r.eigenvalues[j] - want[j]) < 1e-8 * want[p.nev], "complex eigenvalue %d: %.12g vs %.12g", j, r.eigenvalues[j], want[j]);
+    MVC AX(map, size_t(p.blockSize)), XT(X);
+    A.Apply(X, AX);
+    XT.MvScale(std::vector<Z>(r.eigenvalues.begin(), r.eigenvalues.end()));
+    AX.MvAddMv(Z(1.0), AX, Z(-1.0), XT);
+    std::vector<double> rn;
+    AX.MvNorm(rn);
+    for (int j = 0; j < p.nev; ++j) CHECK(rn[j] < 2e-9 * want[p.nev], "complex residual %d = %.3e", j, rn[j]);
+    mx::SerialDenseMatrix<int, Z> G(p.blockSize, p.blockSize);
+    X.MvTransMv(Z(1.0), X, G);
+    for (int j = 0; j < p.nev; ++j)
+      for (int i = 0; i < p.nev; ++i) CHECK(std::abs(G(i, j) - (i == j ? 1.0 : 0.0)) < 1e-8, "X^H X (%d,%d)", i, j);
+    std::printf("complex:     %d iterations, %ld operator columns\n", r.iterations, r.applyA);
+    // generalized Hermitian problem with a diagonal mass matrix and a Jacobi preconditioner
+    DiagZ M, T;
+    M.d.resize(size_t(A.size()));
+    T.d.resize(size_t(A.size()));
+    for (size_t i = 0; i < M.d.size(); ++i) { M.d[i] = 1.0 + 0.4 * std::cos(0.23 * double(i)); T.d[i] = 1.0 / (2 * (A.c[0] + A.c[1] + A.c[2])); }
+    MVC Xg(map, size_t(p.blockSize));
+    p.seed = 99;
+    MxSolverResult rg = SolverC(&A, &M, &T, p).solve(Xg);
+    CHECK(rg.converged == p.nev, "complex generalized: converged %d of %d in %d iterations", rg.converged, p.nev, rg.iterations);
+    MVC AXg(map, size_t(p.blockSize)), MXg(map, size_t(p.blockSize));
+    A.Apply(Xg, AXg);
+    M.Apply(Xg, MXg);
+    MVC MXT(MXg);
+    MXT.MvScale(std::vector<Z>(rg.eigenvalues.begin(), rg.eigenvalues.end()));
+    AXg.MvAddMv(Z(1.0), AXg, Z(-1.0), MXT);
+    std::vector<double> mn;
+    AXg.MvNorm(rn);
+    MXg.MvNorm(mn);
+    for (int j = 0; j < p.nev; ++j) CHECK(rn[j] < 2e-9 * std::max(rg.eigenvalues[j], 0.1 * rg.eigenvalues[p.nev - 1]) * mn[j] * 1.01, "complex generalized residual %d = %.3e", j, rn[j]);
+    std::printf("complex gen: %d iterations, %ld operator columns\n", rg.iterations, rg.applyA);
+  }
   if (failures == 0) std::printf("PASSED\n");
   return failures ? 1 : 0;
 }
