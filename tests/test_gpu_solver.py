@@ -108,20 +108,15 @@ def test_pillbox_eigenvalues_match_scipy(mx, ctx, orc, use_prec):
 @pytest.mark.xfail(strict=False, reason="complex instantiation of the driver is validated on the host multivector "
                                         "(tests/cpp/solver_host_check.cpp); its first GPU run was still pending when the "
                                         "round's GPU budget ran out")
-def test_complex_bloch_eigensolve_matches_analytic_spectrum(mx, ctx, orc):
+def test_complex_bloch_eigensolve_matches_analytic_spectrum():
     """Hermitian instantiation of the driver (MxSolverT<MxAnasaziMV<complex>, complex>) on the Bloch-periodic vacuum
     vector Laplacian (the pencil operator of config C4's class): eigenvalues sum_i (2/h sin((2 pi m_i + phi_i) / (2 N)))^2,
-    three times each (one per field component)."""
-    n, phi = 8, (0.9, -0.4, 0.25)
-    sim = orc.vacuum(n, phase_shifts=phi)
-    A, op, rmap, _ = gpu_matrix(mx, ctx, sim, "vecLapl")
-    assert op.is_complex
-    lam = [np.array([(2 * n * np.sin((2 * np.pi * m + p) / (2 * n))) ** 2 for m in range(n)]) for p in phi]
-    scalar = np.sort((lam[0][:, None, None] + lam[1][None, :, None] + lam[2][None, None, :]).ravel())
-    solver = mx.MxSolver(ctx, A, nev=6, block_size=10, tol=1e-9, max_iters=1000)
-    ev = solver.solve()
-    assert solver.converged == 6
-    np.testing.assert_allclose(ev[:6], np.repeat(scalar[:2], 3), rtol=1e-8)
-    assert solver.eigenvectors.is_complex
-    res, _ = solver.check()
-    assert res[:6].max() < 1e-7
+    three times each (one per field component). Runs in its own process (tests/complex_solve_check.py) so that a fault
+    in this not-yet-exercised path cannot disturb the CUDA context of the other tests."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tests", "complex_solve_check.py")], capture_output=True, text=True,
+                         timeout=300)
+    assert res.returncode == 0 and "COMPLEX SOLVE OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
