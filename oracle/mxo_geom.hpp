@@ -34,8 +34,7 @@ inline int sgn(double v) { return v < 0.0 ? -1 : (v > 0.0 ? 1 : 0); }
 
 // ---------------------------------------------------------------------------------------
 // Shapes: f > 0 inside. MxShape.hpp:143-165: func(p) = sign * f0(Ainv p - Ainv b) with the
-// affine placement x -> A x + b built up by translate / reflect (MxShape.cpp:172-210).
-// Rotations and scalings are not restated (no BASELINE config uses them).
+// affine placement x -> A x + b built up by translate / reflect / rotate / scale (MxShape.cpp:89-210).
 // ---------------------------------------------------------------------------------------
 using R33 = std::array<std::array<double, 3>, 3>;
 inline R33 r33Eye() { return {{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}}; }
@@ -110,6 +109,29 @@ struct Shape {
     Ainv = r33Inv(A);
     Ainvb = Ainv * b;
   }
+  // MxShape.cpp:89-125. The reference fills the cross-product matrix with the opposite sign of the usual convention
+  // (M = -[a]x), so R = I + M sin + M^2 (1 - cos) turns by -angle about the axis; restated literally.
+  void rotate(const D3& axis, double angle, const D3& pivot) {
+    const D3 a = axis / norm(axis);
+    R33 M{{{0, a[2], -a[1]}, {-a[2], 0, a[0]}, {a[1], -a[0], 0}}};
+    const R33 M2 = M * M;
+    R33 R = r33Eye();
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) R[i][j] += M[i][j] * std::sin(angle) + M2[i][j] * (1.0 - std::cos(angle));
+    A = R * A;
+    b = R * (b - pivot) + pivot;
+    Ainv = r33Inv(A);
+    Ainvb = Ainv * b;
+  }
+  void rotate(const D3& axis, double angle) { rotate(axis, angle, b); }   // about the current translation point
+  // MxShape.cpp:158-168
+  void scale(const D3& magnitudes, const D3& origin = D3{0, 0, 0}) {
+    R33 S{{{magnitudes[0], 0, 0}, {0, magnitudes[1], 0}, {0, 0, magnitudes[2]}}};
+    A = S * A;
+    b = S * (b - origin) + origin;
+    Ainv = r33Inv(A);
+    Ainvb = Ainv * b;
+  }
   void invert() { sign *= -1.0; }
 };
 #define MXO_CLONE(T) std::shared_ptr<Shape> clone() const override { return std::make_shared<T>(*this); }
@@ -154,6 +176,15 @@ struct Sphere : Shape {
   double f0(const D3& p) const override { return 1.0 - dot(p, p) / r2; }
   D3 g0(const D3& p) const override { return -2.0 * p / r2; }
   MXO_CLONE(Sphere)
+};
+
+// MxEllipsoid.hpp:31-33,44-50: f = 1 - sum_i p_i^2 / a_i^2
+struct Ellipsoid : Shape {
+  D3 invAxes2;
+  Ellipsoid(D3 loc, D3 axes) : invAxes2{1.0 / (axes[0] * axes[0]), 1.0 / (axes[1] * axes[1]), 1.0 / (axes[2] * axes[2])} { translate(loc); }
+  double f0(const D3& p) const override { return 1.0 - (p[0] * (invAxes2[0] * p[0]) + p[1] * (invAxes2[1] * p[1]) + p[2] * (invAxes2[2] * p[2])); }
+  D3 g0(const D3& p) const override { return {-2.0 * invAxes2[0] * p[0], -2.0 * invAxes2[1] * p[1], -2.0 * invAxes2[2] * p[2]}; }
+  MXO_CLONE(Ellipsoid)
 };
 
 // MxShapeIntersection.hpp:120-136 (min of sub-shape funcs), :186-206 (gradient of the

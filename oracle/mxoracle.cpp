@@ -66,6 +66,16 @@ void* mxo_shape_repeat(void* shape, const double origin[3], const double dir[3],
   return new std::shared_ptr<Shape>(
       new Repeat(shp(shape), {origin[0], origin[1], origin[2]}, {dir[0], dir[1], dir[2]}, step, numPos, numNeg));
 }
+void* mxo_shape_ellipsoid(const double loc[3], const double axes[3]) {
+  return new std::shared_ptr<Shape>(new Ellipsoid({loc[0], loc[1], loc[2]}, {axes[0], axes[1], axes[2]}));
+}
+void mxo_shape_rotate(void* sh, const double axis[3], double angle, const double* pivot) {
+  if (pivot) shp(sh)->rotate({axis[0], axis[1], axis[2]}, angle, {pivot[0], pivot[1], pivot[2]});
+  else shp(sh)->rotate({axis[0], axis[1], axis[2]}, angle);
+}
+void mxo_shape_scale(void* sh, const double mags[3], const double origin[3]) {
+  shp(sh)->scale({mags[0], mags[1], mags[2]}, {origin[0], origin[1], origin[2]});
+}
 void mxo_shape_translate(void* sh, const double v[3]) { shp(sh)->translate({v[0], v[1], v[2]}); }
 void mxo_shape_reflect(void* sh, const double normal[3], const double point[3]) {
   shp(sh)->reflect({normal[0], normal[1], normal[2]}, {point[0], point[1], point[2]});

@@ -42,6 +42,9 @@ def lib():
             "mxo_shape_subtract": (vp, [vp, C.POINTER(vp), C.c_int]),
             "mxo_shape_mirror": (vp, [vp, d3, d3]),
             "mxo_shape_repeat": (vp, [vp, d3, d3, dbl, C.c_int, C.c_int]),
+            "mxo_shape_ellipsoid": (vp, [d3, d3]),
+            "mxo_shape_rotate": (None, [vp, d3, dbl, vp]),
+            "mxo_shape_scale": (None, [vp, d3, d3]),
             "mxo_shape_translate": (None, [vp, d3]),
             "mxo_shape_reflect": (None, [vp, d3, d3]),
             "mxo_shape_grad": (None, [vp, d3, d3]),
@@ -151,6 +154,20 @@ class Shape:
     def repeat(shape, origin, direction, step, num_pos, num_neg):
         return Shape(lib().mxo_shape_repeat(shape.h, _d3(origin), _d3(direction), float(step), int(num_pos), int(num_neg)),
                      keep=(shape,))
+
+    @staticmethod
+    def ellipsoid(loc, axes):
+        return Shape(lib().mxo_shape_ellipsoid(_d3(loc), _d3(axes)))
+
+    def rotate(self, axis, angle, pivot=None):
+        """MxShape::rotate (MxShape.cpp:89-125): about `pivot`, or about the shape's current translation point."""
+        pv = _d3(pivot) if pivot is not None else None
+        lib().mxo_shape_rotate(self.h, _d3(axis), float(angle), C.cast(pv, C.c_void_p) if pv is not None else None)
+        return self
+
+    def scale(self, magnitudes, origin=(0.0, 0.0, 0.0)):
+        lib().mxo_shape_scale(self.h, _d3(magnitudes), _d3(origin))
+        return self
 
     def translate(self, v):
         lib().mxo_shape_translate(self.h, _d3(v))

@@ -122,3 +122,36 @@ def test_crab_cavity_geometry_and_operators(orc):
     w = sla.eigs(L[keep][:, keep].tocsc(), k=4, M=sp.diags(d[keep]).tocsc(), sigma=2000.0, tol=1e-8, return_eigenvectors=False)
     w = np.sort(w.real)
     assert 1500 < w[0] < 6000, w
+
+
+def test_ellipsoid_rotate_scale(orc):
+    """MxEllipsoid.hpp:31-50 and the rotate / scale placements of MxShape.cpp:89-168."""
+    S = orc.Shape
+    e = S.ellipsoid((0.1, 0.0, -0.2), (0.4, 0.2, 0.1))
+    assert e.func((0.1, 0.0, -0.2)) == 1.0
+    assert e.func((0.5, 0.0, -0.2)) == pytest.approx(0.0, abs=1e-15)
+    assert e.func((0.1, 0.2, -0.2)) == pytest.approx(0.0, abs=1e-15) and e.func((0.1, 0.0, -0.1)) == pytest.approx(0.0, abs=1e-15)
+    np.testing.assert_allclose(e.grad((0.3, 0.0, -0.2)), (-2 * 0.2 / 0.16, 0, 0), rtol=1e-13)
+    # a scaled sphere has the same zero level set, hence the same cut-cell fractions
+    s = S.sphere(0.1, (0, 0, 0)).scale((4.0, 2.0, 1.0))
+    e0 = S.ellipsoid((0, 0, 0), (0.4, 0.2, 0.1))
+    for p in [(0.38, 0.02, 0.01), (0.1, 0.17, 0.02), (0.05, 0.05, 0.09)]:
+        for kind, axis, lens in ((0, 0, (0.05,)), (1, 2, (0.05, 0.05)), (2, 0, (0.05, 0.05, 0.05))):
+            assert s.fraction(kind, axis, lens, p) == pytest.approx(e0.fraction(kind, axis, lens, p), abs=1e-10)
+    # rotating a z-cylinder by a quarter turn about y (either sense) gives an x-cylinder
+    for ang in (0.5 * math.pi, -0.5 * math.pi):
+        c = S.cylinder(0.3, (0, 0, 1), (0, 0, 0)).rotate((0, 1, 0), ang)
+        cx = S.cylinder(0.3, (1, 0, 0), (0, 0, 0))
+        for p in [(5.0, 0.1, 0.2), (0.0, 0.3, 0.0), (-2.0, 0.2, 0.25), (0.0, 0.0, 0.31)]:
+            assert c.func(p) == pytest.approx(cx.func(p), abs=1e-14)
+    # sense of rotation as written in the reference (M = -[a]x): +angle about z takes the half-space normal x to -y
+    h = S.halfspace((0, 0, 0), (1, 0, 0)).rotate((0, 0, 1), 0.5 * math.pi)
+    assert h.func((0, -1, 0)) == pytest.approx(1.0) and h.func((1, 0, 0)) == pytest.approx(0.0, abs=1e-15)
+    # rotation about an explicit pivot moves the centre; about the own centre (default pivot) it does not
+    sp = S.sphere(0.2, (1.0, 0.0, 0.0)).rotate((0, 0, 1), math.pi, pivot=(0, 0, 0))
+    assert sp.func((-1.0, 0.0, 0.0)) == pytest.approx(1.0)
+    sp2 = S.sphere(0.2, (1.0, 0.0, 0.0)).rotate((0, 0, 1), 1.234)
+    assert sp2.func((1.0, 0.0, 0.0)) == pytest.approx(1.0)
+    # scaling about an origin moves the centre accordingly
+    sc = S.sphere(0.1, (0.5, 0, 0)).scale((2.0, 2.0, 2.0), origin=(0.25, 0, 0))
+    assert sc.func((0.75, 0, 0)) == pytest.approx(1.0) and sc.func((0.95, 0, 0)) == pytest.approx(0.0, abs=1e-14)
