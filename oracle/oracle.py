@@ -406,6 +406,43 @@ def crabcav(cell_res=10, pad=2, num_cells=4, cell_len=2.0 * 0.0192, cav_rad=0.04
                pec=crabcav_shape(num_cells=num_cells, cell_len=cell_len, cav_rad=cav_rad))
 
 
+def pill_w_tubes(cells_per_iris=4, ph_adv=2.0 * 3.141592653589793 / 3.0):
+    """example/pillWTubes.py:14-150 -- one period of an iris-loaded 12 GHz accelerator structure: pillbox cavity
+    (cylinder ∩ slab) united with the rounded iris tube (cylinder ∩ two inverted tori), periodic in z with the Bloch
+    phase advance `ph_adv` -> complex operators on a Dey-Mittra PEC geometry. cells_per_iris = 4 is the example's grid."""
+    import math
+    c0, mm, ghz = 2.99792458e8, 1.0e-3, 1.0e9
+    omega010 = 2.0 * math.pi * 12.0 * ghz
+    iris_r, iris_t = 3.15 * mm, 1.67 * mm
+    sync_ph_adv = 2.0 * math.pi / 3.0
+    lz = c0 * sync_ph_adv / omega010
+    lz_cav = lz - iris_t
+    # getCavRadius (pillWTubes.py:22-62): first-order perturbation estimate of the iris detuning
+    alpha = math.sqrt((2.405 / iris_r) ** 2 - (omega010 / c0) ** 2)
+    tau = 2.0 / (math.pi * (2.405 * 0.5191) ** 2)
+    t1 = tau * (iris_r ** 3 / (3.0 * lz_cav * c0 ** 2))
+    t1 *= 1.0 - math.cos(sync_ph_adv) * math.exp(-alpha * iris_t)
+    t2 = (math.sqrt(3.0 * 27.0 * t1 ** 4 * omega010 ** 2 + 12.0 * t1 ** 3) + 9.0 * t1 ** 2 * omega010) ** (1.0 / 3.0)
+    omega_pill = t2 / (2.0 ** (1.0 / 3.0) * 3.0 ** (2.0 / 3.0) * t1) - (2.0 / 3.0) ** (1.0 / 3.0) / t2
+    R = c0 * 2.405 / omega_pill
+    zhat, zzz = (0, 0, 1), (0, 0, 0)
+    cyl = Shape.cylinder(R, zhat, zzz)
+    caps = Shape.slab(lz_cav, zhat, (0, 0, 0.5 * lz))
+    pill = Shape.intersection([cyl, caps])
+    iris_cyl = Shape.cylinder(iris_r + 0.5 * iris_t, zhat, zzz)
+    torus1 = Shape.torus(iris_r + 0.5 * iris_t, 0.5 * iris_t, zhat, zzz).invert()
+    torus2 = Shape.torus(iris_r + 0.5 * iris_t, 0.5 * iris_t, zhat, (0, 0, lz)).invert()
+    iris_tube = Shape.intersection([iris_cyl, torus1, torus2])
+    cav = Shape.union([pill, iris_tube])
+    d = iris_t / float(cells_per_iris)
+    lx = 2.0 * R + 4.0 * d
+    nz = int(lz / d) + 1
+    nx = int(lx / d) + 1
+    sim = Sim((nx, nx, nz), origin=(-0.5 * lx, -0.5 * lx, 0.0), size=(lx, lx, lz), phase_shifts=(0.0, 0.0, ph_adv), pec=cav)
+    sim.info = {"R": R, "lz": lz, "iris_r": iris_r, "iris_t": iris_t, "k2_target": (omega010 / c0) ** 2}
+    return sim
+
+
 def dsphmsph(n, eps=10.0, a=0.37, b=0.49, size=1.0, origin=-0.5):
     """example/dsphmsph.py: dielectric sphere (radius a, permittivity eps) inside a PEC sphere (radius b).
     The example runs one octant with PEC/PMC symmetry planes; this helper takes the full ball in a box."""

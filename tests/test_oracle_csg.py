@@ -155,3 +155,28 @@ def test_ellipsoid_rotate_scale(orc):
     # scaling about an origin moves the centre accordingly
     sc = S.sphere(0.1, (0.5, 0, 0)).scale((2.0, 2.0, 2.0), origin=(0.25, 0, 0))
     assert sc.func((0.75, 0, 0)) == pytest.approx(1.0) and sc.func((0.95, 0, 0)) == pytest.approx(0.0, abs=1e-14)
+
+
+def test_iris_loaded_structure_with_bloch_phase(orc):
+    """example/pillWTubes.py: pillbox + rounded iris tube (inverted tori), periodic in z with a 2 pi / 3 phase advance.
+    Dey-Mittra PEC geometry AND complex Bloch factors in one operator; the structure is designed so that the TM010-like
+    mode at that phase advance sits at 12 GHz."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as sla
+    sim = orc.pill_w_tubes(cells_per_iris=2)
+    assert sim.is_complex and sim.n == (28, 28, 10)
+    A = sim.op("curlCurl")
+    assert A.is_complex and np.diff(A.arrays()[0]).max() == 13
+    dB, cE, gP = sim.op("divB").scipy(), sim.op("curlE").scipy(), sim.op("gradPsi").scipy()
+    assert abs(dB @ cE).max() < 1e-9 * abs(cE).max()
+    assert abs(A.scipy() @ gP).max() < 1e-9 * abs(A.scipy()).max() * abs(gP).max()
+    L, M = sim.op("vecLapl").scipy(), sim.op("mRhs").scipy()
+    d = M.diagonal().real
+    keep = np.where(d > 0)[0]
+    target = sim.info["k2_target"]                      # (2 pi 12 GHz / c)^2
+    w = sla.eigs(L[keep][:, keep].tocsc(), k=4, M=sp.diags(d[keep]).tocsc(), sigma=target, tol=1e-9, return_eigenvectors=False)
+    assert abs(w.imag).max() < 1e-6 * target
+    nearest = w.real[np.argmin(abs(w.real - target))]
+    assert abs(nearest - target) / target < 0.03, (nearest, target)
+    # without the phase advance the operators are real
+    assert not orc.pill_w_tubes(cells_per_iris=2, ph_adv=0.0).op("curlCurl").is_complex
