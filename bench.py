@@ -441,6 +441,10 @@ def main():
                 tr = json.load(f).get("%s-%d-%s-%d" % (args.workload, args.size, args.layout, b))
             if tr and world == 1:
                 roof["traffic"] = tr["dram_bytes"]
+                # what actually crosses the HBM interface: far below the roofline, the compressed layout leaves the
+                # kernel bound by L1 data-pipe wavefronts (profiles/README_r01.md)
+                roof["dram_gbs"] = tr["dram_bytes"] / (ms_step * 1e-3) / 1e9
+                roof["dram_frac"] = roof["dram_gbs"] / peak
                 roof["traffic_source"] = ("profiles/r01_traffic.json (%s; ncu capture of the plain row assignment -- the "
                                           "interleaved kernel streams the same arrays)" % tr["kernel"])
         except Exception:
