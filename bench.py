@@ -217,6 +217,8 @@ def main():
     ap.add_argument("--nvec", type=int, default=1)
     ap.add_argument("--no-sweep", action="store_true", help="skip the informational 4- and 10-vector block applies")
     ap.add_argument("--layout", default="dict", choices=["dict", "sell"])
+    ap.add_argument("--order", choices=["ref", "soa"], default="ref",
+                    help="device ordering of the vectors: reference (ascending GID) or component-major (experimental, 1 GPU)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-solve", action="store_true", help="skip the eigensolve leg (seconds to nev eigenpairs)")
@@ -282,7 +284,9 @@ def main():
     my_vals = np.ascontiguousarray(val[p0:p1])
 
     t = time.time()
-    bmap = mx.MxMap(ctx, n_global, my_gids)
+    if args.order == "soa" and world > 1:
+        raise SystemExit("--order soa (component-major device ordering) is single-rank only")
+    bmap = mx.MxMap(ctx, n_global, my_gids, components=3 if args.order == "soa" else 1)
     layout = mx.LAYOUT_DICT if args.layout == "dict" else mx.LAYOUT_SELL
     A = mx.MxCrsMatrix.from_csr(bmap, bmap, my_rowptr, my_cols, my_vals, layout=layout)
     stats = A.stats()
@@ -375,7 +379,7 @@ def main():
     # the same steps through the host-buffer entry point, which pipelines upload / apply / download of successive
     # items over two device slots (every item still crosses the bus both ways inside the timed region)
     e2e_s, e2e_mode = e2e_serial_s, "serial upload -> apply -> download per step"
-    if b == 1:
+    if b == 1 and args.order == "ref":
         yhs = [yh, mx.pinned_array((n_loc, b), dt)]
         x1 = xh[:, 0]
         A.apply_host_batch([x1, x1], [yhs[0][:, 0], yhs[1][:, 0]])
@@ -455,7 +459,8 @@ def main():
             "vs_baseline": None, "dtype": "c128" if is_complex else "f64", "data": "synthetic",
             "config": {"workload": "%s-%d curlCurl SpMV (Dey-Mittra, %d rows, %d nnz)" % (args.workload, args.size, nrows_g, nnz_g),
                        "nvec": b, "layout": args.layout, "l2": "inputs_larger_than_l2" if layout_bytes > 126e6 else "fits_l2",
-                       "partition": "x-slab x%d" % world, "gen_s": info["gen_s"], "layout_build_s": round(build_s, 2)},
+                       "partition": "x-slab x%d" % world, "gen_s": info["gen_s"], "layout_build_s": round(build_s, 2),
+                       "vector_order": "component-major" if args.order == "soa" else "reference (ascending GID)"},
             "layout": stats,
             "roofline": roof,
             "cpu_baseline": cpu,

@@ -109,7 +109,10 @@ struct mxg_map {
   mxg_ctx* ctx = nullptr;
   int64_t nGlobal = 0, nLocal = 0;
   std::vector<int64_t> gids;           // host copy (ascending)
-  int64_t* dGids = nullptr;            // device copy (RNG keys, halo plans)
+  int64_t* dGids = nullptr;            // device copy (RNG keys, halo plans); in DEVICE order when the map is ordered
+  // Optional component-major device ordering (mxg_map_create_ordered): perm[device position] = reference local index,
+  // inv = its inverse. Empty = device order is the reference order (ascending GID).
+  std::vector<int32_t> perm, inv;
   int refs = 1;
 };
 

@@ -176,3 +176,17 @@ def test_host_buffer_batch_apply(mx, ctx, orc, is_complex):
         if not is_complex:
             assert np.array_equal(ys[i], op.apply(xs[i])), i
     A.apply_host_batch([], [])
+
+
+@pytest.mark.xfail(strict=False, reason="component-major ordered maps: host half validated on the CPU (tests/test_ilv_model.py); "
+                                        "the device half was written after the round's GPU budget ran out and has not run yet")
+def test_component_major_ordered_maps():
+    """mxg_map_create_ordered: vectors stored component-major on the device, operators re-indexed at creation. Results must
+    equal the reference order bit for bit. Runs in its own process (tests/ordered_map_check.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tests", "ordered_map_check.py")], capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0 and "ORDERED MAPS OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
