@@ -88,3 +88,24 @@ def test_eigvals_to_freqs(mx):
     f2 = mx.eigvals_to_freqs(mu, shift=shift, invert=True)
     np.testing.assert_allclose(f2.real, f[:3].real, rtol=1e-13)
     assert mx.eigvals_to_freqs([]).shape == (0,)
+
+
+def test_error_convention_without_gpu(mx):
+    """Every entry point returns an int status and leaves a message in mxg_last_error / mxs_last_error (SURVEY section 8b:
+    the reference prints and exit()s; the C ABI reports). Argument validation does not need a device."""
+    import ctypes as C
+    L = mx.load_library()
+    S = mx.load_solver()
+    assert L.mxg_mv_norm2(None, None) < 0 and b"NULL" in L.mxg_last_error()
+    assert L.mxg_crs_apply(None, None, None) < 0 and b"mxg_crs_apply" in L.mxg_last_error()
+    h = C.c_void_p()
+    assert L.mxg_map_create(None, 10, None, 0, C.byref(h)) < 0
+    assert L.mxg_map_create_ordered(None, 10, None, 0, 99, C.byref(h)) < 0 and b"ncomp" in L.mxg_last_error()
+    assert L.mxg_mv_to_grid(None, 0, 0, 0, None, None) < 0
+    assert L.mxg_crs_apply_host_batch(None, 1, None, None) < 0
+    assert L.mxg_gmg_apply(None, None, None) < 0
+    assert S.mxs_lobpcg(None, None, None, None, None, None, None, None, None, None) != 0
+    assert b"NULL" in S.mxs_last_error()
+    assert S.mxs_magwave_apply(None, None, None, None, None, None, None, None, 0.0, 1e-8, 1, None, None, None) != 0
+    assert S.mxs_mag_to_elec(None, None, None, None, None) != 0
+    assert S.mxs_eigvals_to_freqs(None, None, 3, 0.0, 0, None, None) != 0 and b"bad argument" in S.mxs_last_error()
