@@ -254,7 +254,10 @@ static int allocMv(mxg_map* map, int ncols, bool isComplex, bool zero, mxg_mv** 
   mxg_ctx* ctx = map->ctx;
   MXG_CUDA(cudaSetDevice(ctx->device));
   const size_t esz = isComplex ? 16 : 8;
-  const size_t bytes = size_t(map->nLocal) * ncols * esz;
+  // columns start on 256-byte boundaries (the bulk copies of the windowed SpMM need 16-byte aligned sources; kernels
+  // take column pointers, so the stride is invisible outside this file)
+  const size_t colBytes = (size_t(map->nLocal) * esz + 255) / 256 * 256;
+  const size_t bytes = colBytes * ncols;
   auto st = std::make_shared<MvStorage>();
   st->ctx = ctx;
   st->bytes = bytes;
@@ -272,7 +275,7 @@ static int allocMv(mxg_map* map, int ncols, bool isComplex, bool zero, mxg_mv** 
   mv->col.resize(ncols);
   mv->baseCol.resize(ncols);
   for (int j = 0; j < ncols; ++j) {
-    mv->col[j] = static_cast<char*>(st->base) + size_t(j) * map->nLocal * esz;
+    mv->col[j] = static_cast<char*>(st->base) + size_t(j) * colBytes;
     mv->baseCol[j] = j;
   }
   *out = mv;

@@ -174,6 +174,12 @@ struct mxg_crs {
   // and domain maps coincide -- the smoothers of the multigrid cycle use it
   void* dInvDiag = nullptr;
   int ilv = 1;                         // dictionary kernel: thread -> row interleave (1 or 3)
+  // windowed dictionary kernel (mxg_spmm_win.cuh): per-tile x windows staged in shared memory by 1-D TMA
+  void* dWinTiles = nullptr;           // WinTile[winTiles]
+  int winR = 0;                        // rows per tile (0 = windowed path off)
+  int winIlv = 1;                      // thread -> row assignment inside a tile (1 or 3)
+  int64_t winTiles = 0, winValid = 0;  // tiles / tiles served from shared memory
+  int64_t winBufElems = 0;             // largest window set of any tile (scalars)
   // captured CUDA graphs of the multi-rank apply (pack -> NCCL exchange || interior rows -> boundary rows),
   // keyed by the operand pointers; replaying one costs a single launch instead of ~10 enqueues
   struct GraphEntry {

@@ -26,6 +26,7 @@
 #include "mxg_internal.h"
 #include "mxg_ilv_model.h"
 #include "mxg_order.h"
+#include "mxg_spmm_win.cuh"
 
 using namespace mxg;
 
@@ -213,6 +214,101 @@ __global__ void __launch_bounds__(kBlockIlv) k_spmm_dict_ilv3(int64_t rowBegin, 
   if (row < rowEnd) dictRow<T, GHOST, NV>(row, D, X, Y, nvec, ep);
 }
 
+
+// ---- windowed dictionary kernel (design notes: mxg_spmm_win.cuh) ------------------------------------------------------
+// One CTA per tile of R = kWinThreads * RPT consecutive rows. Thread 0 arms an mbarrier and issues <= 3 bulk copies that
+// bring the tile's x windows into shared memory; meanwhile every thread fetches the pattern ids of its rows. For a block of
+// vectors the windows of vector j+1 are loaded into the second buffer while vector j is being consumed.
+// ILV = 3: warp w of a 384-row sub-tile takes rows 3*lane + (w mod 3) of its 96-row group -- 32 consecutive cells of ONE
+// field component, which share a pattern (one broadcast load per entry) and read shared memory with stride 3 (no bank
+// conflict). ILV = 1: lane = consecutive row (scalar fields).
+template <class T>
+__device__ __forceinline__ void winIssue(const WinTile& W, const T* __restrict__ xcol, T* buf, uint64_t* bar) {
+  uint32_t bytes = 0;
+#pragma unroll
+  for (int sgi = 0; sgi < 3; ++sgi) bytes += uint32_t(W.segLen[sgi]) * uint32_t(sizeof(T));
+  mbarExpectTx(bar, bytes);
+  int off = 0;
+#pragma unroll
+  for (int sgi = 0; sgi < 3; ++sgi) {
+    if (W.segLen[sgi] > 0) bulkLoad(buf + off, xcol + W.segLo[sgi], uint32_t(W.segLen[sgi]) * uint32_t(sizeof(T)), bar);
+    off += W.segLen[sgi];
+  }
+}
+
+template <class T, int ILV, int RPT>
+__global__ void __launch_bounds__(kWinThreads) k_spmm_win(int64_t rowBegin, int64_t rowEnd, int64_t tile0, DictArgs<T> D,
+                                                          const WinTile* __restrict__ tiles, int bufElems, int nbuf, XSource<T> X,
+                                                          ColTable<T> Y, int nvec, Epilogue<T> ep) {
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smemRaw);          // two barriers
+  WinTile* Ws = reinterpret_cast<WinTile*>(smemRaw + 64);
+  T* buf = reinterpret_cast<T*>(smemRaw + 128);
+  constexpr int R = kWinThreads * RPT;
+  const int64_t tile = tile0 + blockIdx.x;
+  if (threadIdx.x == 0) {
+    const int4* src = reinterpret_cast<const int4*>(tiles + tile);
+    int4* dst = reinterpret_cast<int4*>(Ws);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = __ldg(src + i);
+    mbarInit(&bar[0], 1);
+    mbarInit(&bar[1], 1);
+    mbarFenceInit();
+    if (Ws->valid) winIssue<T>(*Ws, X.x.p[0], buf, &bar[0]);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tOff = ILV == 3 ? (warp / 3) * 96 + 3 * lane + (warp % 3) : int(threadIdx.x);
+  int64_t row[RPT];
+  int32_t o[RPT], oe[RPT];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    row[i] = tile * R + i * kWinThreads + tOff;
+    o[i] = oe[i] = 0;
+    if (row[i] >= rowBegin && row[i] < rowEnd) {
+      const int32_t p = D.rowPat[row[i]];
+      if (p >= 0) { o[i] = __ldg(D.patOff + p); oe[i] = __ldg(D.patOff + p + 1); }
+    }
+  }
+  __syncthreads();
+  if (!Ws->valid) {   // tile-uniform: gather path
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+      if (row[i] >= rowBegin && row[i] < rowEnd) dictRow<T, false, 1>(row[i], D, X, Y, nvec, ep);
+    return;
+  }
+  const int32_t dLo = Ws->dLo, dHi = Ws->dHi, s0 = Ws->shift[0], s1 = Ws->shift[1], s2 = Ws->shift[2];
+  for (int j = 0; j < nvec; ++j) {
+    const int b = nbuf == 2 ? (j & 1) : 0;
+    if (nbuf == 2 && j + 1 < nvec && threadIdx.x == 0) winIssue<T>(*Ws, X.x.p[j + 1], buf + ((j + 1) & 1) * bufElems, &bar[(j + 1) & 1]);
+    mbarWait(&bar[b], nbuf == 2 ? ((j >> 1) & 1) : (j & 1));
+    const T* __restrict__ xs = buf + b * bufElems;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      if (oe[i] == o[i]) continue;
+      const int32_t r = int32_t(row[i]);
+      T acc = zeroOf<T>();
+      int32_t q = o[i];
+      for (; q + 1 < oe[i]; q += 2) {
+        const PatEntry<T> e0 = D.pat[q];
+        const PatEntry<T> e1 = D.pat[q + 1];
+        const T x0 = xs[r + e0.d + (e0.d < dLo ? s0 : (e0.d > dHi ? s2 : s1))];
+        const T x1 = xs[r + e1.d + (e1.d < dLo ? s0 : (e1.d > dHi ? s2 : s1))];
+        accum(acc, entryVal(e0), x0);
+        accum(acc, entryVal(e1), x1);
+      }
+      if (q < oe[i]) {
+        const PatEntry<T> e0 = D.pat[q];
+        accum(acc, entryVal(e0), xs[r + e0.d + (e0.d < dLo ? s0 : (e0.d > dHi ? s2 : s1))]);
+      }
+      storeY(Y.p[j], row[i], acc, ep);
+    }
+    if (j + 1 < nvec) {
+      __syncthreads();   // everyone is done with this buffer
+      if (nbuf == 1 && threadIdx.x == 0) winIssue<T>(*Ws, X.x.p[j + 1], buf, &bar[0]);
+    }
+  }
+}
+
 template <class T, bool GHOST, int NV>
 __global__ void __launch_bounds__(kBlock) k_spmm_sell(int64_t genBegin, int64_t genEnd, SellArgs<T> S,
                                                       XSource<T> X, ColTable<T> Y, int nvec, Epilogue<T> ep) {
@@ -303,6 +399,41 @@ int launchSegments(const mxg_crs* A, const int64_t b[4], const int64_t e[4], con
   return MXG_OK;
 }
 
+
+// rows per thread of the windowed kernel (tile = kWinThreads * RPT rows)
+template <class T> struct WinCfg;
+template <> struct WinCfg<double> { static constexpr int RPT = 4; };
+template <> struct WinCfg<zd> { static constexpr int RPT = 2; };
+constexpr size_t kWinSmemHeader = 128;
+constexpr size_t kWinSmemMax = 200 * 1024;      // per CTA, both buffers
+constexpr size_t kWinBufBudget = 100 * 1024;    // one window set
+
+template <class T>
+int launchWin(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, const XSource<T>& X, const ColTable<T>& Y, int nvec,
+              const Epilogue<T>& ep, cudaStream_t st) {
+  mxg_ctx* ctx = A->ctx;
+  constexpr int RPT = WinCfg<T>::RPT;
+  const int R = A->winR;
+  const int64_t tile0 = rowBegin / R, tiles = (rowEnd + R - 1) / R - tile0;
+  const size_t bufBytes = size_t(A->winBufElems) * sizeof(T);
+  const int nbuf = (nvec > 1 && kWinSmemHeader + 2 * bufBytes <= kWinSmemMax) ? 2 : 1;
+  const size_t smem = kWinSmemHeader + nbuf * bufBytes;
+  const DictArgs<T> D = dictArgs<T>(A);
+  const WinTile* wt = static_cast<const WinTile*>(A->dWinTiles);
+  static bool attrSet[2] = {false, false};
+  if (A->winIlv == 3) {
+    auto kern = k_spmm_win<T, 3, RPT>;
+    if (!attrSet[0]) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWinSmemMax))); attrSet[0] = true; }
+    kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, D, wt, int(A->winBufElems), nbuf, X, Y, nvec, ep);
+  } else {
+    auto kern = k_spmm_win<T, 1, RPT>;
+    if (!attrSet[1]) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWinSmemMax))); attrSet[1] = true; }
+    kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, D, wt, int(A->winBufElems), nbuf, X, Y, nvec, ep);
+  }
+  LAUNCH_CHECK(ctx);
+  return MXG_OK;
+}
+
 template <class T, bool GHOST>
 int launchRange(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, int64_t genBegin, int64_t genEnd, const XSource<T>& X,
                 const ColTable<T>& Y, int nvec, const Epilogue<T>& ep, cudaStream_t st = nullptr) {
@@ -314,7 +445,10 @@ int launchRange(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, int64_t genB
   // merged kernel (launchBoundary).
   const bool prof = ctx->profiling;
   if (prof) MXG_CUDA(cudaEventRecord(ctx->prof[1], ctx->stream));
-  if (A->dictRows > 0 && rowEnd > rowBegin) {
+  if (A->dictRows > 0 && rowEnd > rowBegin && A->winR > 0) {
+    const int rc = launchWin<T>(A, rowBegin, rowEnd, X, Y, nvec, ep, st);
+    if (rc) return rc;
+  } else if (A->dictRows > 0 && rowEnd > rowBegin) {
     const DictArgs<T> D = dictArgs<T>(A);
     if (A->ilv == 3) {
       const int64_t blocks = (rowEnd - rowBegin + kBlockIlv - 1) / kBlockIlv;
@@ -950,6 +1084,41 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
     }
   }
 
+  // ---- windowed dictionary kernel: per-tile x windows (mxg_spmm_win.cuh). MXG_SPMV_WIN=0 keeps the gather kernels.
+  {
+    const char* env = std::getenv("MXG_SPMV_WIN");
+    const bool want = !(env && std::strcmp(env, "0") == 0);
+    if (want && A->dictRows > 0 && nLoc + A->gLo + A->gHi < (int64_t(1) << 30)) {
+      constexpr int R = kWinThreads * WinCfg<T>::RPT;
+      constexpr int align = 16 / int(sizeof(T)) > 0 ? 16 / int(sizeof(T)) : 1;
+      const PatEntry<T>* pe = pat.data();
+      int64_t maxTotal = 0, valid = 0;
+      std::vector<WinTile> tiles = planWinTiles(rowPat.data(), patOff.data(), A->numPats, [pe](int32_t q) { return int64_t(pe[q].d); }, nRows,
+                                                nLoc, R, align, int64_t(kWinBufBudget / sizeof(T)), &maxTotal, &valid);
+      if (valid > 0) {
+        WinTile* dT = nullptr;
+        if ((rc = uploadVec(tiles, &dT, &A->deviceBytes, ctx))) return rc;
+        A->dWinTiles = dT;
+        A->winR = R;
+        A->winTiles = int64_t(tiles.size());
+        A->winValid = valid;
+        A->winBufElems = maxTotal;
+        // thread -> row assignment: component triples (GID = comp + 3 cell) share patterns at distance 3, scalar fields at 1
+        int64_t same1 = 0, same3 = 0;
+        for (int64_t r = 0; r + 3 < nRows; ++r) {
+          if (rowPat[r] < 0) continue;
+          same1 += rowPat[r] == rowPat[r + 1];
+          same3 += rowPat[r] == rowPat[r + 3];
+        }
+        A->winIlv = same3 > same1 ? 3 : 1;
+        if (const char* iv = std::getenv("MXG_SPMV_ILV")) {
+          if (std::strcmp(iv, "1") == 0) A->winIlv = 1;
+          if (std::strcmp(iv, "3") == 0) A->winIlv = 3;
+        }
+      }
+    }
+  }
+
   // ---- general rows in sliced ELL; the three row classes (leading boundary, interior,
   // trailing boundary) each start on a slice boundary so they can be launched separately
   std::vector<int32_t> genRow, genLen;
@@ -1085,7 +1254,7 @@ int mxg_crs_destroy(mxg_crs* A) {
   if (A->p2p.flags) cudaFree(A->p2p.flags);
   if (A->p2p.epoch) cudaFree(A->p2p.epoch);
   if (A->p2p.done) cudaFree(A->p2p.done);
-  void* ptrs[] = {A->dRowPat, A->dPatOff, A->dPat, A->dGenRow, A->dGenLen, A->dSlicePtr, A->dCol, A->dVal, A->dSendIdx, A->dSendBuf, A->dGhost, A->dInvDiag};
+  void* ptrs[] = {A->dRowPat, A->dPatOff, A->dPat, A->dGenRow, A->dGenLen, A->dSlicePtr, A->dCol, A->dVal, A->dSendIdx, A->dSendBuf, A->dGhost, A->dInvDiag, A->dWinTiles};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   mxg_map_destroy(A->rowMap);
