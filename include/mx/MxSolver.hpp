@@ -348,13 +348,20 @@ struct MxSolverParams {
   uint64_t seed = 12345;
   bool randomInit = true;  // MxSolver.cpp:62-64 starts from MvRandom
   bool profile = false;    // per-phase wall times (synchronises around each phase)
+  // constrained solves (MxSolverT::setConstraint): relative accuracy of the inner projection solves
+  double projTolInit = 1e-10;   // initial block
+  double projTolW = 1e-2;       // preconditioned residuals, every iteration
+  double projTolX = 1e-3;       // re-projection of the iterate when its constraint violation becomes visible
+  double reprojectRatio = 0.05; // re-project X when violation > ratio * max(relative residual, tol)
 };
 
 struct MxSolverResult {
   std::vector<double> eigenvalues, residuals;   // blockSize entries, ascending
   int iterations = 0, converged = 0;
   long applyA = 0, applyPrec = 0;
-  double tApplyA = 0, tPrec = 0, tGram = 0, tUpdate = 0;   // filled when params.profile is set (adds syncs)
+  long projections = 0, reprojections = 0;                  // constraint projections (columns) / re-projections of X
+  std::vector<double> violation;                            // |D M x_j| / |M x_j| of the returned vectors (constrained solves)
+  double tApplyA = 0, tPrec = 0, tGram = 0, tUpdate = 0, tProj = 0;   // filled when params.profile is set (adds syncs)
   double seconds = 0.0;
 };
 
@@ -375,6 +382,12 @@ class MxSolverT {
     if (p_.blockSize < p_.nev) p_.blockSize = p_.nev;
     if (3 * p_.blockSize > MXG_MAX_COLS) throw std::runtime_error("MxSolver: block size too large (3*block must be <= 128)");
   }
+
+  // Keep the iteration inside a constraint subspace (the divergence-free fields: MxDivProjector). The reference gets the
+  // same effect from the projection inside MxMagWaveOp::Apply (MxMagWaveOp.cpp:893-924), which removes the gradient
+  // fields -- the grad-div part of vecLapl's spectrum -- from every Krylov vector.
+  void setConstraint(const mx::Constraint<S>* c) { C_ = c; }
+  MxSolverParams& params() { return p_; }
 
   // X: n x blockSize. On return holds the Ritz vectors (M-orthonormal), ascending eigenvalues.
   MxSolverResult solve(MV& X) {
@@ -423,6 +436,7 @@ class MxSolverT {
       auto x = view(Sb, xc);
       if (p_.randomInit) { X.setSeed(p_.seed); X.MvRandom(); }
       *x = X;
+      if (C_) { timeit(res.tProj, [&] { C_->project(*x, p_.projTolInit); }); res.projections += m; }
       auto mx_ = view(MSb, xc);
       applyM(*x, *mx_);
     }
@@ -493,6 +507,7 @@ class MxSolverT {
       theta = w;
     }
     int np = 0;  // columns currently in the P block
+    bool forceExplicit = false;   // next Rayleigh-Ritz forms the full Gram matrices (after X was re-projected)
     std::vector<double> relres(m, 1.0);
     int it = 0;
     for (; it < p_.maxIters; ++it) {
@@ -515,6 +530,47 @@ class MxSolverT {
         for (int j = 0; j < m; ++j) {
           const double den = std::max(std::fabs(theta[j]), 0.1 * thetaRef) * mn[j];
           relres[j] = den > 0 ? rn[j] / den : rn[j];
+        }
+      }
+      if (C_) {
+        // constraint violation of the iterate, |D M x_j| / |M x_j|. The projected search directions keep it from
+        // growing, but what the inexact projections let through stays in X: remove it once it is visible next to
+        // the residual, then refresh the images of X.
+        auto mxv = view(MSb, xc);
+        std::vector<double> viol, mn;
+        C_->violation(*mxv, viol);
+        mxv->MvNorm(mn);
+        double worst = 0.0;
+        for (int j = 0; j < m; ++j) {
+          viol[j] = mn[j] > 0 ? viol[j] / mn[j] : 0.0;
+          worst = std::max(worst, viol[j] / std::max(relres[j], p_.tol));
+        }
+        res.violation = viol;
+        if (worst > p_.reprojectRatio) {
+          auto x = view(Sb, xc);
+          auto ax = view(ASb, xc);
+          timeit(res.tProj, [&] { C_->project(*x, p_.projTolX); });
+          res.projections += m;
+          ++res.reprojections;
+          applyM(*x, *mxv);
+          timeit(res.tApplyA, [&] { A_->Apply(*x, *ax); });
+          res.applyA += m;
+          forceExplicit = true;
+          if (p_.verbose) std::printf("MxSolver iter %3d  re-projected X (violation / residual = %.2e)\n", it, worst);
+          // residuals of the cleaned iterate
+          auto scaled = view(tmp, range(m, m));
+          *scaled = *mxv;
+          scaled->MvScale(std::vector<S>(theta.begin(), theta.end()));
+          R->MvAddMv(S(1.0), *ax, S(-1.0), *scaled);
+          std::vector<double> rn;
+          R->MvNorm(rn);
+          mxv->MvNorm(mn);
+          double thetaRef = 0.0;
+          for (int j = 0; j < p_.nev; ++j) thetaRef = std::max(thetaRef, std::fabs(theta[j]));
+          for (int j = 0; j < m; ++j) {
+            const double den = std::max(std::fabs(theta[j]), 0.1 * thetaRef) * mn[j];
+            relres[j] = den > 0 ? rn[j] / den : rn[j];
+          }
         }
       }
       std::vector<int> active;
@@ -540,6 +596,7 @@ class MxSolverT {
         auto W = view(Sb, wc);
         if (T_) { timeit(res.tPrec, [&] { T_->Apply(*Ra, *W); }); res.applyPrec += na; }
         else *W = *Ra;
+        if (C_) { timeit(res.tProj, [&] { C_->project(*W, p_.projTolW); }); res.projections += na; }
         auto MW = view(MSb, wc);
         applyM(*W, *MW);
         // W <- W - X (X^T M W)
@@ -572,7 +629,8 @@ class MxSolverT {
         ns = int(sc.size());
         std::vector<S> ga, gm;
         const int nwb = int(wc.size());
-        if (it % 10 == 0) {
+        if (it % 10 == 0 || forceExplicit) {
+          forceExplicit = false;
           // explicit Gram matrices of the whole basis (also resets the round-off drift of the implicit ones)
           Dense GA = gram(Sb, sc, ASb, sc), GM = gram(Sb, sc, MSb, sc);
           ga = toVec(GA);
@@ -659,54 +717,358 @@ class MxSolverT {
   const mx::Operator<S>* A_;
   const mx::Operator<S>* M_;
   const mx::Operator<S>* T_;
+  const mx::Constraint<S>* C_ = nullptr;
   MxSolverParams p_;
 };
 typedef MxSolverT<MxAnasaziMV<double>> MxSolver;
 
+// ---- inner Krylov solvers of MxMagWaveOp (src/MxMagWaveOp.cpp:285-353: AztecOO GMRES / CG / BiCGStab) ----------------
+// Block versions on the GPU multivector: every column runs its own recurrence, all columns share the kernels. Work
+// vectors are allocated once per (map, width) and reused by later solves. Per iteration the O(n) work is the operator,
+// the preconditioner, per-column fused updates (mxg_mv_axpby_cols) and two or three block reductions.
+namespace mx {
+enum LinSolverType { LIN_CG = 0, LIN_BICGSTAB = 1, LIN_GMRES = 2 };   // "linear solver : type" (MxMagWaveOp.cpp:326-338)
+
+template <class S>
+class BlockKrylov {
+ public:
+  typedef MxAnasaziMV<S> MV;
+  typedef std::function<void(const MV&, MV&)> Fn;
+  typedef ScalarTraits<S> ST;
+
+  // x = A^-1 b to |r_j| <= tol |b_j| for every column; returns the iteration count. prec may be empty.
+  long solve(LinSolverType type, const Fn& A, const Fn& prec, const MV& b, MV& x, double tol, int maxIters, int basis = 20) {
+    switch (type) {
+      case LIN_CG: return pcg(A, prec, b, x, tol, maxIters);
+      case LIN_BICGSTAB: return bicgstab(A, prec, b, x, tol, maxIters);
+      default: return gmres(A, prec, b, x, tol, maxIters, basis);
+    }
+  }
+
+  long pcg(const Fn& A, const Fn& prec, const MV& b, MV& x, double tol, int maxIters) {
+    const int nb = b.GetNumberVecs();
+    reserve(b, nb, 4);
+    MV &r = *w_[0], &z = *w_[1], &p = *w_[2], &q = *w_[3];
+    const std::vector<S> one(nb, S(1.0));
+    x.MvInit(S(0.0));
+    r = b;
+    std::vector<double> bn, rn;
+    std::vector<S> rz(nb), rzNew(nb), pq(nb), alpha(nb), malpha(nb), beta(nb);
+    b.MvNorm(bn);
+    auto precond = [&](const MV& in, MV& out) { if (prec) prec(in, out); else out = in; };
+    precond(r, z);
+    p = z;
+    r.MvDot(z, rz);   // rz_j = z_j^H r_j; real for a Hermitian positive definite preconditioner
+    long it = 0;
+    rn = bn;
+    for (; it < maxIters; ++it) {
+      if (converged(rn, bn, tol)) break;
+      A(p, q);
+      q.MvDot(p, pq);   // p^H q
+      for (int j = 0; j < nb; ++j) {
+        const bool live = rn[j] > tol * bn[j] && std::abs(pq[j]) > 0.0;
+        alpha[j] = live ? rz[j] / pq[j] : S(0.0);
+        malpha[j] = -alpha[j];
+      }
+      axpbyCols(x, one, x, alpha, p);
+      axpbyCols(r, one, r, malpha, q);
+      r.MvNorm(rn);
+      if (converged(rn, bn, tol)) { ++it; break; }
+      precond(r, z);
+      r.MvDot(z, rzNew);
+      for (int j = 0; j < nb; ++j) { beta[j] = std::abs(rz[j]) > 0.0 ? rzNew[j] / rz[j] : S(0.0); rz[j] = rzNew[j]; }
+      axpbyCols(p, one, z, beta, p);
+    }
+    return it;
+  }
+
+  // right-preconditioned BiCGStab (van der Vorst); for shifts inside the spectrum, where L - sigma M is indefinite
+  long bicgstab(const Fn& A, const Fn& prec, const MV& b, MV& x, double tol, int maxIters) {
+    const int nb = b.GetNumberVecs();
+    reserve(b, nb, 8);
+    MV &r = *w_[0], &r0 = *w_[1], &p = *w_[2], &v = *w_[3], &y = *w_[4], &sv = *w_[5], &z = *w_[6], &t = *w_[7];
+    const std::vector<S> one(nb, S(1.0));
+    auto precond = [&](const MV& in, MV& out) { if (prec) prec(in, out); else out = in; };
+    x.MvInit(S(0.0));
+    r = b;
+    r0 = b;
+    p.MvInit(S(0.0));
+    v.MvInit(S(0.0));
+    std::vector<double> bn, rn;
+    b.MvNorm(bn);
+    rn = bn;
+    std::vector<S> rho(nb, S(1.0)), alpha(nb, S(1.0)), omega(nb, S(1.0)), rhoNew(nb), c1(nb), c2(nb), r0v(nb), ts(nb), tt(nb);
+    long it = 0;
+    for (; it < maxIters; ++it) {
+      if (converged(rn, bn, tol)) break;
+      r.MvDot(r0, rhoNew);   // r0^H r
+      for (int j = 0; j < nb; ++j) {
+        const bool live = rn[j] > tol * bn[j] && std::abs(rho[j]) > 0.0 && std::abs(omega[j]) > 0.0;
+        const S beta = live ? (rhoNew[j] / rho[j]) * (alpha[j] / omega[j]) : S(0.0);
+        c1[j] = beta;
+        c2[j] = -beta * omega[j];
+      }
+      axpbyCols(p, c1, p, c2, v);     // p = beta (p - omega v)
+      axpbyCols(p, one, r, one, p);   //   + r
+      precond(p, y);
+      A(y, v);
+      v.MvDot(r0, r0v);
+      for (int j = 0; j < nb; ++j) {
+        const bool live = rn[j] > tol * bn[j] && std::abs(r0v[j]) > 0.0;
+        alpha[j] = live ? rhoNew[j] / r0v[j] : S(0.0);
+        c1[j] = -alpha[j];
+      }
+      axpbyCols(sv, one, r, c1, v);   // s = r - alpha v
+      precond(sv, z);
+      A(z, t);
+      sv.MvDot(t, ts);   // t^H s
+      t.MvDot(t, tt);
+      for (int j = 0; j < nb; ++j) {
+        omega[j] = std::abs(tt[j]) > 0.0 ? ts[j] / tt[j] : S(0.0);
+        if (!(rn[j] > tol * bn[j])) omega[j] = S(0.0);
+        c2[j] = -omega[j];
+        rho[j] = rhoNew[j];
+      }
+      axpbyCols(x, one, x, alpha, y);
+      axpbyCols(x, one, x, omega, z);
+      axpbyCols(r, one, sv, c2, t);   // r = s - omega t
+      r.MvNorm(rn);
+    }
+    return it;
+  }
+
+  // right-preconditioned restarted GMRES(basis), the reference's default ("linear solver : type" = gmres,
+  // "linear solver : basis" = 20; MxMagWaveOp.cpp:326-345). Modified Gram-Schmidt, Givens rotations per column.
+  long gmres(const Fn& A, const Fn& prec, const MV& b, MV& x, double tol, int maxIters, int m) {
+    const int nb = b.GetNumberVecs();
+    reserve(b, nb, m + 3);
+    MV &w = *w_[m + 1], &zt = *w_[m + 2];
+    const std::vector<S> one(nb, S(1.0));
+    auto precond = [&](const MV& in, MV& out) { if (prec) prec(in, out); else out = in; };
+    x.MvInit(S(0.0));
+    std::vector<double> bn, rn;
+    b.MvNorm(bn);
+    rn = bn;
+    long it = 0;
+    std::vector<S> coef(nb), mcoef(nb);
+    while (it < maxIters && !converged(rn, bn, tol)) {
+      // r = b - A x into V0, normalised
+      MV& V0 = *w_[0];
+      if (it == 0) V0 = b;
+      else { A(x, w); V0.MvAddMv(S(1.0), b, S(-1.0), w); }
+      V0.MvNorm(rn);
+      if (converged(rn, bn, tol)) break;
+      for (int j = 0; j < nb; ++j) coef[j] = rn[j] > 0.0 ? S(1.0 / rn[j]) : S(0.0);
+      V0.MvScale(coef);
+      std::vector<std::vector<S>> H(nb, std::vector<S>(size_t(m + 1) * m, S(0.0))), g(nb, std::vector<S>(m + 1, S(0.0)));
+      std::vector<std::vector<S>> cs(nb, std::vector<S>(m, S(0.0))), sn(nb, std::vector<S>(m, S(0.0)));
+      for (int j = 0; j < nb; ++j) g[j][0] = rn[j];
+      int k = 0;
+      for (; k < m && it < maxIters; ++k, ++it) {
+        precond(*w_[k], zt);
+        A(zt, w);
+        for (int i = 0; i <= k; ++i) {
+          w.MvDot(*w_[i], coef);   // V_i^H w
+          for (int j = 0; j < nb; ++j) { H[j][i + size_t(k) * (m + 1)] = coef[j]; mcoef[j] = -coef[j]; }
+          axpbyCols(w, one, w, mcoef, *w_[i]);
+        }
+        std::vector<double> hn;
+        w.MvNorm(hn);
+        for (int j = 0; j < nb; ++j) { H[j][(k + 1) + size_t(k) * (m + 1)] = hn[j]; coef[j] = hn[j] > 0.0 ? S(1.0 / hn[j]) : S(0.0); }
+        *w_[k + 1] = w;
+        w_[k + 1]->MvScale(coef);
+        bool all = true;
+        for (int j = 0; j < nb; ++j) {
+          S* h = &H[j][size_t(k) * (m + 1)];
+          for (int i = 0; i < k; ++i) {
+            const S t0 = ST::conj(cs[j][i]) * h[i] + ST::conj(sn[j][i]) * h[i + 1];
+            h[i + 1] = -sn[j][i] * h[i] + cs[j][i] * h[i + 1];
+            h[i] = t0;
+          }
+          const double den = std::sqrt(std::norm(h[k]) + std::norm(h[k + 1]));
+          if (den > 0.0) { cs[j][k] = h[k] / den; sn[j][k] = h[k + 1] / den; }
+          else { cs[j][k] = S(1.0); sn[j][k] = S(0.0); }
+          h[k] = ST::conj(cs[j][k]) * h[k] + ST::conj(sn[j][k]) * h[k + 1];
+          h[k + 1] = S(0.0);
+          g[j][k + 1] = -sn[j][k] * g[j][k];
+          g[j][k] = ST::conj(cs[j][k]) * g[j][k];
+          rn[j] = std::abs(g[j][k + 1]);
+          all = all && (bn[j] == 0.0 || rn[j] <= tol * bn[j]);
+        }
+        if (all) { ++k; ++it; break; }
+      }
+      // y = H^-1 g (upper triangular), x += T (V y)
+      w.MvInit(S(0.0));
+      std::vector<std::vector<S>> yv(nb, std::vector<S>(k, S(0.0)));
+      for (int j = 0; j < nb; ++j)
+        for (int i = k - 1; i >= 0; --i) {
+          S acc = g[j][i];
+          for (int l = i + 1; l < k; ++l) acc -= H[j][i + size_t(l) * (m + 1)] * yv[j][l];
+          const S d = H[j][i + size_t(i) * (m + 1)];
+          yv[j][i] = std::abs(d) > 0.0 ? acc / d : S(0.0);
+        }
+      for (int i = 0; i < k; ++i) {
+        for (int j = 0; j < nb; ++j) coef[j] = yv[j][i];
+        axpbyCols(w, one, w, coef, *w_[i]);
+      }
+      precond(w, zt);
+      x.MvAddMv(S(1.0), x, S(1.0), zt);
+    }
+    return it;
+  }
+
+ private:
+  static bool converged(const std::vector<double>& rn, const std::vector<double>& bn, double tol) {
+    for (size_t j = 0; j < rn.size(); ++j)
+      if (!(bn[j] == 0.0 || rn[j] <= tol * bn[j])) return false;
+    return true;
+  }
+  static void axpbyCols(MV& dst, const std::vector<S>& a, const MV& A, const std::vector<S>& b, const MV& B) {
+    mx::check(mxg_mv_axpby_cols(dst.getRawMV(), reinterpret_cast<const double*>(a.data()), A.getRawMV(),
+                                reinterpret_cast<const double*>(b.data()), B.getRawMV()));
+  }
+  // `count` work multivectors of nb columns on b's map: views of cached allocations of the widest block seen so far
+  void reserve(const MV& b, int nb, int count) {
+    mxg_map* raw = b.getMap()->raw();
+    if (raw != rawMap_ || nb > width_ || count > int(full_.size())) {
+      if (raw != rawMap_ || nb > width_) { full_.clear(); width_ = std::max(nb, raw == rawMap_ ? width_ : 0); }
+      rawMap_ = raw;
+      while (int(full_.size()) < count) full_.emplace_back(new MV(b.getMap(), size_t(width_)));
+    }
+    w_.clear();
+    std::vector<size_t> cols(nb);
+    std::iota(cols.begin(), cols.end(), size_t(0));
+    for (int i = 0; i < count; ++i) w_.emplace_back(new MV(*full_[i], cols, false));
+  }
+  std::vector<std::unique_ptr<MV>> full_, w_;
+  mxg_map* rawMap_ = nullptr;
+  int width_ = 0;
+};
+
+}  // namespace mx
+
+// ---- the divergence-cleaning projection of MxMagWaveOp::Apply (src/MxMagWaveOp.cpp:893-924) --------------------------
+//   P b = b + gradPsi * scaLapl^-1 * divB * M * b,   scaLapl = -(divB M gradPsi) (:208-223)
+// P is the M-orthogonal projector onto { b : divB M b = 0 }: it removes the gradient fields, i.e. the grad-div part of the
+// spectrum of vecLapl. The scalar system is solved by block preconditioned CG (V-cycle on the scalar hierarchy, or
+// Jacobi); on a closed cavity / periodic box scaLapl is singular with the constant in its null space -- harmless here,
+// only gradPsi * psi is used and gradPsi annihilates constants.
+template <class Scalar>
+class MxDivProjector : public mx::Operator<Scalar>, public mx::Constraint<Scalar> {
+  typedef MxAnasaziMV<Scalar> MV;
+
+ public:
+  MxDivProjector(mxg_crs* divB, mxg_crs* gradPsi, mxg_crs* scaLapl, mxg_mv* mDiag, const mx::Operator<Scalar>* scaPrec,
+                 std::shared_ptr<MxComm> comm, double tol = 1e-10, int maxIters = 500)
+      : D_(divB), G_(gradPsi), S_(scaLapl), m_(mDiag), Ts_(scaPrec), comm_(comm), tol_(tol), maxIters_(maxIters) {
+    pmap_.reset(new MxMap(mxg_crs_row_map(D_), comm_, false));
+  }
+  mutable long numApplies = 0, numColumns = 0, numLinIters = 0;
+
+  void Apply(const mx::MultiVec<Scalar>& x, mx::MultiVec<Scalar>& y) const override {   // y = P x (x may be y)
+    MV& y2 = dynamic_cast<MV&>(y);
+    if (&x != &y) y2 = dynamic_cast<const MV&>(x);
+    project(y, tol_);
+  }
+  void project(mx::MultiVec<Scalar>& b, double tol) const override {
+    MV& b2 = dynamic_cast<MV&>(b);
+    const int nb = b2.GetNumberVecs();
+    ensure(b2, nb);
+    MV rhs(*rhsFull_, cols(nb), false), psi1(*psi1Full_, cols(nb), false), psi2(*psi2Full_, cols(nb), false);
+    if (m_) mx::check(mxg_mv_diag_mult(rhs.getRawMV(), m_, b2.getRawMV()));                 // y = mRhs bWork (:895)
+    else rhs = b2;
+    mx::check(mxg_crs_apply(D_, rhs.getRawMV(), psi1.getRawMV()));                           // psi1 = divB y (:896)
+    typename mx::BlockKrylov<Scalar>::Fn A = [&](const MV& in, MV& out) { mx::check(mxg_crs_apply(S_, in.getRawMV(), out.getRawMV())); };
+    typename mx::BlockKrylov<Scalar>::Fn T;
+    if (Ts_) T = [&](const MV& in, MV& out) { Ts_->Apply(in, out); };
+    else T = [&](const MV& in, MV& out) { mx::check(mxg_crs_jacobi(S_, in.getRawMV(), out.getRawMV())); };
+    numLinIters += krylov_.pcg(A, T, psi1, psi2, tol, maxIters_);                            // (:903-913)
+    const double one[2] = {1.0, 0.0};
+    mx::check(mxg_crs_apply_axpby(G_, one, psi2.getRawMV(), one, b2.getRawMV()));            // y = gradPsi psi2 + bWork (:919-921)
+    ++numApplies;
+    numColumns += nb;
+  }
+  void violation(const mx::MultiVec<Scalar>& Mb, std::vector<double>& out) const override {
+    const MV& m2 = dynamic_cast<const MV&>(Mb);
+    const int nb = m2.GetNumberVecs();
+    ensure(m2, nb);
+    MV psi1(*psi1Full_, cols(nb), false);
+    mx::check(mxg_crs_apply(D_, m2.getRawMV(), psi1.getRawMV()));
+    psi1.MvNorm(out);
+  }
+
+ private:
+  static std::vector<size_t> cols(int n) { std::vector<size_t> c(n); std::iota(c.begin(), c.end(), size_t(0)); return c; }
+  void ensure(const MV& b, int nb) const {
+    if (nb <= width_) return;
+    width_ = nb;
+    rhsFull_.reset(new MV(b.getMap(), size_t(nb)));
+    psi1Full_.reset(new MV(pmap_, size_t(nb)));
+    psi2Full_.reset(new MV(pmap_, size_t(nb)));
+  }
+  mxg_crs *D_, *G_, *S_;
+  mxg_mv* m_;
+  const mx::Operator<Scalar>* Ts_;
+  std::shared_ptr<MxComm> comm_;
+  std::shared_ptr<MxMap> pmap_;
+  double tol_;
+  int maxIters_;
+  mutable mx::BlockKrylov<Scalar> krylov_;
+  mutable std::unique_ptr<MV> rhsFull_, psi1Full_, psi2Full_;
+  mutable int width_ = 0;
+};
+
 // ---- MxMagWaveOp (src/MxMagWaveOp.{h,cpp}): the shift-invert operator the reference hands to Anasazi ------
 //   Apply:  y = P (L - sigma M)^-1 M x            (MxMagWaveOp.cpp:825-943)
-//   with L = vecLapl, M = mRhs (diagonal), and the divergence-cleaning projection
-//   P b = b + gradPsi * scaLapl^-1 * divB * M * b  (:893-924), scaLapl = -(divB M gradPsi) (:208-223).
-// The reference solves both systems with AztecOO GMRES/CG + ML or ILUT (:285-537). Here both are block
-// preconditioned CG on the GPU (valid for sigma below the lowest eigenvalue -- the reference's default
-// automatic shift 0.05 (2 pi / L)^2, src/mx.py:711-712 -- where L - sigma M is positive definite), with the
-// multigrid V-cycle as the vector preconditioner and Jacobi (or a second V-cycle) for the scalar solve.
+// with L = vecLapl, M = mRhs (diagonal) and the projection P above. The reference solves the vector system with AztecOO
+// GMRES / CG / BiCGStab + ML or ILUT (:285-537); here: block CG (sigma below the spectrum -- the reference's automatic
+// shift 0.05 (2 pi / L)^2, src/mx.py:711-712 -- where L - sigma M is positive definite), BiCGStab or restarted GMRES (any
+// shift), all preconditioned by the multigrid V-cycle. Scalar = double or MxComplex (Bloch-periodic operators).
 struct MxMagWaveOpParams {
   double shift = 0.0;          // sigma
   double linTol = 1e-10;       // "linear solver : tol" on |r| / |b|
   int maxLinIters = 1000;
   bool hasCurlNull = true;     // 3-D: project out the gradient fields
+  mx::LinSolverType linSolver = mx::LIN_CG;   // "linear solver : type"
+  int linBasis = 20;           // "linear solver : basis" (GMRES restart length)
 };
 
-class MxMagWaveOp : public mx::Operator<double> {
-  typedef MxAnasaziMV<double> MV;
+template <class Scalar>
+class MxMagWaveOpT : public mx::Operator<Scalar> {
+  typedef MxAnasaziMV<Scalar> MV;
 
  public:
-  MxMagWaveOp(mxg_crs* vecLapl, mxg_mv* mDiag, mxg_crs* divB, mxg_crs* gradPsi, mxg_crs* scaLapl,
-              const mx::Operator<double>* vecPrec, const mx::Operator<double>* scaPrec, MxMagWaveOpParams p)
-      : L_(vecLapl), m_(mDiag), D_(divB), G_(gradPsi), S_(scaLapl), Tv_(vecPrec), Ts_(scaPrec), p_(p) {}
+  MxMagWaveOpT(mxg_crs* vecLapl, mxg_mv* mDiag, mxg_crs* divB, mxg_crs* gradPsi, mxg_crs* scaLapl,
+               const mx::Operator<Scalar>* vecPrec, const mx::Operator<Scalar>* scaPrec, std::shared_ptr<MxComm> comm, MxMagWaveOpParams p)
+      : L_(vecLapl), m_(mDiag), Tv_(vecPrec), p_(p) {
+    if (p_.hasCurlNull) proj_.reset(new MxDivProjector<Scalar>(divB, gradPsi, scaLapl, mDiag, scaPrec, comm, p.linTol, p.maxLinIters));
+  }
 
   // counters the reference prints from its destructor (MxMagWaveOp.cpp:96-115)
-  mutable long numApplies = 0, numVecLinIters = 0, numScaLinIters = 0;
+  mutable long numApplies = 0, numVecLinIters = 0;
+  long numScaLinIters() const { return proj_ ? proj_->numLinIters : 0; }
 
-  void Apply(const mx::MultiVec<double>& x, mx::MultiVec<double>& y) const override {
+  void Apply(const mx::MultiVec<Scalar>& x, mx::MultiVec<Scalar>& y) const override {
     const MV& x2 = dynamic_cast<const MV&>(x);
     MV& y2 = dynamic_cast<MV&>(y);
     ++numApplies;
     const int nb = x2.GetNumberVecs();
-    std::shared_ptr<MxMap> bmap = x2.getMap();
-    MV rhs(bmap, nb), bWork(bmap, nb);
+    if (nb > width_) { width_ = nb; rhsFull_.reset(new MV(x2.getMap(), size_t(nb))); tFull_.reset(new MV(x2.getMap(), size_t(nb))); }
+    std::vector<size_t> c(nb);
+    std::iota(c.begin(), c.end(), size_t(0));
+    MV rhs(*rhsFull_, c, false), tmp(*tFull_, c, false);
     mx::check(mxg_mv_diag_mult(rhs.getRawMV(), m_, x2.getRawMV()));                       // y = mRhs x (:865)
-    numVecLinIters += pcg([&](const MV& in, MV& out) { applyShifted(in, out); }, Tv_, nullptr, rhs, bWork);   // (:869-885)
-    if (!p_.hasCurlNull) { y2 = bWork; return; }
-    mx::check(mxg_mv_diag_mult(rhs.getRawMV(), m_, bWork.getRawMV()));                    // y = mRhs bWork (:895)
-    std::shared_ptr<MxMap> pmap(new MxMap(mxg_crs_row_map(D_), bmap->getComm(), false));
-    MV psi1(pmap, nb), psi2(pmap, nb);
-    mx::check(mxg_crs_apply(D_, rhs.getRawMV(), psi1.getRawMV()));                         // psi1 = divB y (:896)
-    numScaLinIters += pcg([&](const MV& in, MV& out) { mx::check(mxg_crs_apply(S_, in.getRawMV(), out.getRawMV())); },
-                          Ts_, S_, psi1, psi2);                                             // (:903-913)
-    mx::check(mxg_crs_apply(G_, psi2.getRawMV(), y2.getRawMV()));                          // y = gradPsi psi2 (:919)
-    y2.MvAddMv(1.0, y2, 1.0, bWork);                                                        // y += bWork (:921)
+    typename mx::BlockKrylov<Scalar>::Fn A = [&](const MV& in, MV& out) {                   // out = (L - sigma M) in
+      mx::check(mxg_crs_apply(L_, in.getRawMV(), out.getRawMV()));
+      if (p_.shift != 0.0) {
+        mx::check(mxg_mv_diag_mult(tmp.getRawMV(), m_, in.getRawMV()));
+        out.MvAddMv(Scalar(1.0), out, Scalar(-p_.shift), tmp);
+      }
+    };
+    typename mx::BlockKrylov<Scalar>::Fn T;
+    if (Tv_) T = [&](const MV& in, MV& out) { Tv_->Apply(in, out); };
+    numVecLinIters += krylov_.solve(p_.linSolver, A, T, rhs, y2, p_.linTol, p_.maxLinIters, p_.linBasis);   // (:869-885)
+    if (proj_) proj_->project(y2, p_.linTol);                                               // (:893-924)
   }
 
   // E = [invEps] curlB B (MxMagWaveOp.cpp:1237-1250). invEps may be NULL (no dielectric).
@@ -728,56 +1090,13 @@ class MxMagWaveOp : public mx::Operator<double> {
   }
 
  private:
-  void applyShifted(const MV& in, MV& out) const {   // out = (L - sigma M) in
-    mx::check(mxg_crs_apply(L_, in.getRawMV(), out.getRawMV()));
-    if (p_.shift != 0.0) {
-      MV t(in.getMap(), in.GetNumberVecs());
-      mx::check(mxg_mv_diag_mult(t.getRawMV(), m_, in.getRawMV()));
-      out.MvAddMv(1.0, out, -p_.shift, t);
-    }
-  }
-  // block preconditioned CG, one independent recurrence per column; returns the iteration count.
-  // prec == nullptr and jac != nullptr: Jacobi with the operator's diagonal; both null: unpreconditioned.
-  template <class ApplyA>
-  long pcg(ApplyA&& A, const mx::Operator<double>* prec, mxg_crs* jac, const MV& b, MV& x) const {
-    const int nb = b.GetNumberVecs();
-    std::shared_ptr<MxMap> map = b.getMap();
-    MV r(b), z(map, nb), pdir(map, nb), q(map, nb), tmp(map, nb);
-    x.MvInit(0.0);
-    std::vector<double> bn, rn, rz(nb), rzNew(nb), pq(nb), alpha(nb), beta(nb);
-    b.MvNorm(bn);
-    auto precond = [&](const MV& in, MV& out) {
-      if (prec) prec->Apply(in, out);
-      else if (jac) mx::check(mxg_crs_jacobi(jac, in.getRawMV(), out.getRawMV()));
-      else out = in;
-    };
-    precond(r, z);
-    pdir = z;
-    r.MvDot(z, rz);
-    long it = 0;
-    for (; it < p_.maxLinIters; ++it) {
-      r.MvNorm(rn);
-      bool done = true;
-      for (int j = 0; j < nb; ++j) done = done && (bn[j] == 0.0 || rn[j] <= p_.linTol * bn[j]);
-      if (done) break;
-      A(pdir, q);
-      pdir.MvDot(q, pq);
-      for (int j = 0; j < nb; ++j) alpha[j] = pq[j] != 0.0 ? rz[j] / pq[j] : 0.0;
-      tmp = pdir; tmp.MvScale(alpha); x.MvAddMv(1.0, x, 1.0, tmp);
-      tmp = q; tmp.MvScale(alpha); r.MvAddMv(1.0, r, -1.0, tmp);
-      precond(r, z);
-      r.MvDot(z, rzNew);
-      for (int j = 0; j < nb; ++j) { beta[j] = rz[j] != 0.0 ? rzNew[j] / rz[j] : 0.0; rz[j] = rzNew[j]; }
-      pdir.MvScale(beta);
-      pdir.MvAddMv(1.0, pdir, 1.0, z);
-    }
-    return it;
-  }
-
   mxg_crs* L_;
   mxg_mv* m_;
-  mxg_crs *D_, *G_, *S_;
-  const mx::Operator<double>* Tv_;
-  const mx::Operator<double>* Ts_;
+  const mx::Operator<Scalar>* Tv_;
   MxMagWaveOpParams p_;
+  std::unique_ptr<MxDivProjector<Scalar>> proj_;
+  mutable mx::BlockKrylov<Scalar> krylov_;
+  mutable std::unique_ptr<MV> rhsFull_, tFull_;
+  mutable int width_ = 0;
 };
+typedef MxMagWaveOpT<double> MxMagWaveOp;

@@ -103,4 +103,15 @@ class Operator {
   virtual void Apply(const MultiVec<Scalar>& x, MultiVec<Scalar>& y) const = 0;
 };
 
+// A constraint the eigensolver keeps its search space in (MxSolverT::setConstraint): the divergence-free subspace.
+template <class S>
+class Constraint {
+ public:
+  virtual ~Constraint() {}
+  // b <- P b in place; the inner solve reduces its residual by `tol`
+  virtual void project(MultiVec<S>& b, double tol) const = 0;
+  // out[j] = |D M b_j|_2 given Mb = M b (the reference's checkDivergences, MxMagWaveOp.cpp:1211-1234)
+  virtual void violation(const MultiVec<S>& Mb, std::vector<double>& out) const = 0;
+};
+
 }  // namespace mx

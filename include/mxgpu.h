@@ -117,6 +117,15 @@ int mxg_mv_conj(mxg_mv* mv);
 int mxg_mv_update(mxg_mv* dst, const double a[2], const mxg_mv* A, const double s[2]);
 /* MvAddMv: dst = alpha*A + beta*B; A and/or B may alias dst (MxAnasaziMV.cpp:89-111) */
 int mxg_mv_add_mv(mxg_mv* dst, const double alpha[2], const mxg_mv* A, const double beta[2], const mxg_mv* B);
+/* dst_j = alphas[j]*A_j + betas[j]*B_j: MvAddMv with one scalar pair per column (as MvScale(vector), MxAnasaziMV.hpp:110-118,
+ * followed by MvAddMv, MxAnasaziMV.cpp:89-111, in one pass); alphas/betas: ncols scalars; A and/or B may alias dst */
+int mxg_mv_axpby_cols(mxg_mv* dst, const double* alphas, const mxg_mv* A, const double* betas, const mxg_mv* B);
+/* removeConstField (MxGeoMultigridPrec.cpp:400-411, MxUtil.cpp:483-503): x_j -= (x_j . 1)/(1 . 1) 1 for every column;
+ * reduction, all-reduce and update run back to back on the device */
+int mxg_mv_remove_const_field(mxg_mv* mv);
+/* MxGridField::zeroUnusedComponents (MxGridField.cpp:548-576; applied to the initial block at MxSolver.cpp:65):
+ * zero the entries whose shape fraction is 0; fracs = one-column multivector on the same map */
+int mxg_mv_zero_unused(mxg_mv* mv, const mxg_mv* fracs);
 /* norm2 / MvNorm (MxMultiVector.cpp:148-155): out[ncols] */
 int mxg_mv_norm2(const mxg_mv* mv, double* out);
 /* dot / MvDot: out[j] = conj(a_j) . b_j  (out: ncols scalars, complex interleaved). This is
@@ -203,6 +212,8 @@ typedef struct mxg_gmg_params {
   double coarse_eig_ratio;
   int full_multigrid;       /* 1: fullVCycle (FMG), 0: plain V-cycles from a zero guess     */
   int power_iterations;     /* iterations of the lambda_max(D^-1 A) estimate at setup       */
+  int remove_const_field;   /* 1: project the constant out after every coarsen / refine ("remove const field",
+                               MxGeoMultigridPrec.cpp:108,438-452): singular scalar Laplacians    */
 } mxg_gmg_params;
 void mxg_gmg_default_params(mxg_gmg_params* p);
 int mxg_gmg_create(mxg_ctx* ctx, int nlevels, mxg_crs* const* ops, mxg_crs* const* restrictors,

@@ -18,6 +18,21 @@ typedef struct mxs_params {
   int random_init;  /* 1: start from MvRandom (MxSolver.cpp:62-64), 0: use X as given */
 } mxs_params;
 
+/* The divergence-cleaning projection of MxMagWaveOp::Apply (MxMagWaveOp.cpp:893-924), P b = b + gradPsi scaLapl^-1 divB M b,
+ * as a constraint of the eigensolver: the iteration stays in { b : divB M b = 0 }, so only Maxwell modes are returned
+ * (the reference gets the same from applying P inside its shift-invert operator). */
+typedef struct mxs_projection {
+  mxg_crs* divB;          /* psi <- B  (MxYeeDeyMittraDivB) */
+  mxg_crs* gradPsi;       /* B <- psi  (MxYeeDeyMittraGradPsi) */
+  mxg_crs* scaLapl;       /* -(divB M gradPsi) (MxMagWaveOp.cpp:208-223) */
+  mxg_gmg* sca_prec;      /* multigrid on the scalar hierarchy, or NULL = Jacobi */
+  double tol_init;        /* relative accuracy of the inner CG: initial block (0 = 1e-10) */
+  double tol_w;           /* ... preconditioned residuals, every iteration (0 = 1e-2) */
+  double tol_x;           /* ... re-projection of the iterate (0 = 1e-3) */
+  double reproject_ratio; /* re-project X when |D M x|/|M x| > ratio * max(relative residual, tol) (0 = 0.05) */
+  int max_iters;          /* inner CG iteration cap (0 = 500) */
+} mxs_projection;
+
 void mxs_default_params(mxs_params* p);
 const char* mxs_last_error(void);
 /* per-phase seconds of the last mxs_lobpcg call made with verbose >= 2 (which synchronises around phases):
@@ -31,6 +46,16 @@ void mxs_last_profile(double out[4]);
  * [3]=preconditioner applies (columns). */
 int mxs_lobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, mxg_mv* X, const mxs_params* p,
                double* evals, double* resnorms, int64_t info[4], double* seconds);
+/* Same solver constrained to the divergence-free fields (mxs_projection above): what MxSolver::solve returns in the reference
+ * (MxSolver.cpp:85-103 on MxMagWaveOp::Apply). violation[j] = |divB M x_j| / |M x_j| of the returned vectors (may be NULL).
+ * info[0..3] as mxs_lobpcg, [4] = projected columns, [5] = re-projections of the iterate, [6] = inner CG iterations,
+ * [7] = projection calls. */
+int mxs_lobpcg_projected(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, const mxs_projection* proj, mxg_mv* X,
+                         const mxs_params* p, double* evals, double* resnorms, double* violation, int64_t info[8], double* seconds);
+/* X <- P X alone; info[0] = inner CG iterations */
+int mxs_div_project(mxg_ctx* ctx, mxg_mv* m_diag, const mxs_projection* proj, double tol, mxg_mv* X, int64_t info[1]);
+/* out[0..3] as mxs_last_profile, out[4] = constraint projections */
+void mxs_last_profile_ex(double out[8]);
 /* acceptance metrics of MxMagWaveOp::checkEigensolution / checkDivergences (MxMagWaveOp.cpp:1118-1234):
  * res[j] = |A x_j - theta_j M x_j|_2 / |theta_j| ; div[j] = |D M x_j|_2 / |M x_j|_2 (D may be NULL) */
 int mxs_check_eigensolution(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_crs* divB, mxg_mv* X, const double* evals,
@@ -42,6 +67,12 @@ int mxs_check_eigensolution(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_crs* d
 int mxs_magwave_apply(mxg_ctx* ctx, mxg_crs* vec_lapl, mxg_mv* m_diag, mxg_crs* divB, mxg_crs* gradPsi, mxg_crs* scaLapl,
                       mxg_gmg* vec_prec, mxg_gmg* sca_prec, double shift, double lin_tol, int has_curl_null,
                       mxg_mv* X, mxg_mv* Y, int64_t info[2]);
+/* Same with the inner solver of the vector system chosen as in "linear solver : type" (MxMagWaveOp.cpp:326-338):
+ * lin_solver 0 = CG, 1 = BiCGStab, 2 = restarted GMRES(lin_basis) -- the last two accept shifts inside the spectrum.
+ * Real or complex (Bloch-periodic) operands. lin_basis / max_iters 0 = defaults (20 / 1000). */
+int mxs_magwave_apply_ex(mxg_ctx* ctx, mxg_crs* vec_lapl, mxg_mv* m_diag, mxg_crs* divB, mxg_crs* gradPsi, mxg_crs* scaLapl,
+                         mxg_gmg* vec_prec, mxg_gmg* sca_prec, double shift, double lin_tol, int has_curl_null, int lin_solver,
+                         int lin_basis, int max_iters, mxg_mv* X, mxg_mv* Y, int64_t info[2]);
 /* MxMagWaveOp::magToElec (MxMagWaveOp.cpp:1237-1250): elec = [invEps] curlB mag; invEps NULL when there is no dielectric. */
 int mxs_mag_to_elec(mxg_ctx* ctx, mxg_crs* curlB, mxg_crs* invEps, mxg_mv* mag, mxg_mv* elec);
 /* MxMagWaveOp::eigValsToFreqs (MxMagWaveOp.cpp:1252-1271): f = sqrt(k2) c / 2 pi [Hz], k2 = ev + shift, or 1/ev + shift for the

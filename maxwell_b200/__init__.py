@@ -78,6 +78,9 @@ def load_library():
         "mxg_mv_conj": (i32, [vp]),
         "mxg_mv_update": (i32, [vp, dp, vp, dp]),
         "mxg_mv_add_mv": (i32, [vp, dp, vp, dp, vp]),
+        "mxg_mv_axpby_cols": (i32, [vp, vp, vp, vp, vp]),
+        "mxg_mv_remove_const_field": (i32, [vp]),
+        "mxg_mv_zero_unused": (i32, [vp, vp]),
         "mxg_mv_norm2": (i32, [vp, vp]),
         "mxg_mv_dot": (i32, [vp, vp, vp]),
         "mxg_mv_normalize": (i32, [vp]),
@@ -119,13 +122,21 @@ _SOLVER = None
 class GmgParams(C.Structure):
     """mxg_gmg_params (include/mxgpu.h)."""
     _fields_ = [("smoother_degree", C.c_int), ("eig_ratio", C.c_double), ("cycles", C.c_int), ("coarse_degree", C.c_int),
-                ("coarse_eig_ratio", C.c_double), ("full_multigrid", C.c_int), ("power_iterations", C.c_int)]
+                ("coarse_eig_ratio", C.c_double), ("full_multigrid", C.c_int), ("power_iterations", C.c_int),
+                ("remove_const_field", C.c_int)]
 
 
 class SolverParams(C.Structure):
     """mxs_params (include/mxsolver.h)."""
     _fields_ = [("nev", C.c_int), ("block_size", C.c_int), ("max_iters", C.c_int), ("tol", C.c_double), ("verbose", C.c_int),
                 ("seed", C.c_uint64), ("random_init", C.c_int)]
+
+
+class Projection(C.Structure):
+    """mxs_projection (include/mxsolver.h): the divergence-cleaning projection as an eigensolver constraint."""
+    _fields_ = [("divB", C.c_void_p), ("gradPsi", C.c_void_p), ("scaLapl", C.c_void_p), ("sca_prec", C.c_void_p),
+                ("tol_init", C.c_double), ("tol_w", C.c_double), ("tol_x", C.c_double), ("reproject_ratio", C.c_double),
+                ("max_iters", C.c_int)]
 
 
 def load_solver():
@@ -154,6 +165,15 @@ def load_solver():
     S.mxs_magwave_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp, vp]
     S.mxs_last_profile.restype = None
     S.mxs_last_profile.argtypes = [vp]
+    S.mxs_last_profile_ex.restype = None
+    S.mxs_last_profile_ex.argtypes = [vp]
+    S.mxs_lobpcg_projected.restype = C.c_int
+    S.mxs_lobpcg_projected.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dp]
+    S.mxs_div_project.restype = C.c_int
+    S.mxs_div_project.argtypes = [vp, vp, vp, C.c_double, vp, vp]
+    S.mxs_magwave_apply_ex.restype = C.c_int
+    S.mxs_magwave_apply_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       vp, vp, vp]
     _SOLVER = S
     return S
 
@@ -372,6 +392,21 @@ class MxMultiVector:
     def assign(self, src):
         _ck(self._L.mxg_mv_assign(self.h, src.h))
 
+    def axpby_cols(self, alphas, A, betas, B):
+        """this_j = alphas[j] * A_j + betas[j] * B_j (per-column scalars; A and / or B may be this)."""
+        a = np.ascontiguousarray(alphas, dtype=self.dtype)
+        b = np.ascontiguousarray(betas, dtype=self.dtype)
+        assert len(a) == len(b) == self.GetNumberVecs()
+        _ck(self._L.mxg_mv_axpby_cols(self.h, a.ctypes.data, A.h, b.ctypes.data, B.h))
+
+    def remove_const_field(self):
+        """removeConstField (MxGeoMultigridPrec.cpp:400-411): subtract each column's mean."""
+        _ck(self._L.mxg_mv_remove_const_field(self.h))
+
+    def zero_unused(self, fracs):
+        """MxGridField::zeroUnusedComponents (MxGridField.cpp:548-576): zero the entries whose shape fraction is 0."""
+        _ck(self._L.mxg_mv_zero_unused(self.h, fracs.h))
+
     def normalize(self):
         _ck(self._L.mxg_mv_normalize(self.h))
 
@@ -556,7 +591,7 @@ class MxGeoMultigridPrec:
     """
 
     def __init__(self, ctx, ops, restrictors, prolongators, smoother_sweeps=2, cycles=1, eig_ratio=30.0,
-                 coarse_degree=30, coarse_eig_ratio=1000.0, full_multigrid=False, power_iterations=30):
+                 coarse_degree=30, coarse_eig_ratio=1000.0, full_multigrid=False, power_iterations=30, remove_const_field=False):
         self._L = load_library()
         self._keep = (list(ops), list(restrictors), list(prolongators))
         p = GmgParams()
@@ -564,6 +599,7 @@ class MxGeoMultigridPrec:
         p.smoother_degree, p.cycles, p.eig_ratio = int(smoother_sweeps), int(cycles), float(eig_ratio)
         p.coarse_degree, p.coarse_eig_ratio = int(coarse_degree), float(coarse_eig_ratio)
         p.full_multigrid, p.power_iterations = int(bool(full_multigrid)), int(power_iterations)
+        p.remove_const_field = int(bool(remove_const_field))
         n = len(ops)
         arr = lambda xs: (C.c_void_p * max(len(xs), 1))(*[x.h for x in xs])
         h = C.c_void_p()
@@ -593,9 +629,13 @@ class MxSolver:
     Real symmetric pencils, or Hermitian ones (complex operator of a Bloch-periodic simulation: complex multivectors,
     m_diag a complex one-column multivector)."""
 
-    def __init__(self, ctx, A, m_diag=None, prec=None, nev=10, block_size=0, tol=1e-8, max_iters=300, verbose=0, seed=12345):
+    def __init__(self, ctx, A, m_diag=None, prec=None, nev=10, block_size=0, tol=1e-8, max_iters=300, verbose=0, seed=12345,
+                 projection=None):
+        """projection: dict(divB=, gradPsi=, scaLapl=, sca_prec=None, tol_w=..., tol_x=..., tol_init=..., reproject_ratio=...)
+        constrains the iteration to the divergence-free fields (MxMagWaveOp.cpp:893-924): only Maxwell modes are returned."""
         self._S = load_solver()
         self.ctx, self.A, self.m_diag, self.prec = ctx, A, m_diag, prec
+        self.projection = projection
         p = SolverParams()
         self._S.mxs_default_params(C.byref(p))
         p.nev, p.block_size, p.tol, p.max_iters, p.verbose, p.seed = int(nev), int(block_size), float(tol), int(max_iters), int(verbose), int(seed)
@@ -614,9 +654,25 @@ class MxSolver:
         rs = np.zeros(m)
         info = (C.c_int64 * 4)()
         sec = C.c_double()
-        rc = self._S.mxs_lobpcg(self.ctx.h, self.A.h, self.m_diag.h if self.m_diag is not None else None,
-                                self.prec.h if self.prec is not None else None, X.h, C.byref(self.params),
-                                ev.ctypes.data, rs.ctypes.data, info, C.byref(sec))
+        if self.projection is None:
+            rc = self._S.mxs_lobpcg(self.ctx.h, self.A.h, self.m_diag.h if self.m_diag is not None else None,
+                                    self.prec.h if self.prec is not None else None, X.h, C.byref(self.params),
+                                    ev.ctypes.data, rs.ctypes.data, info, C.byref(sec))
+            self.violation = None
+        else:
+            pr = self.projection
+            P = Projection()
+            P.divB, P.gradPsi, P.scaLapl = pr["divB"].h, pr["gradPsi"].h, pr["scaLapl"].h
+            P.sca_prec = pr["sca_prec"].h if pr.get("sca_prec") is not None else None
+            P.tol_init, P.tol_w, P.tol_x = float(pr.get("tol_init", 0)), float(pr.get("tol_w", 0)), float(pr.get("tol_x", 0))
+            P.reproject_ratio, P.max_iters = float(pr.get("reproject_ratio", 0)), int(pr.get("max_iters", 0))
+            info = (C.c_int64 * 8)()
+            viol = np.zeros(m)
+            rc = self._S.mxs_lobpcg_projected(self.ctx.h, self.A.h, self.m_diag.h if self.m_diag is not None else None,
+                                              self.prec.h if self.prec is not None else None, C.byref(P), X.h, C.byref(self.params),
+                                              ev.ctypes.data, rs.ctypes.data, viol.ctypes.data, info, C.byref(sec))
+            self.violation = viol
+            self.projected_columns, self.reprojections, self.proj_cg_iters, self.proj_calls = info[4], info[5], info[6], info[7]
         if rc != 0:
             raise MxError(self._S.mxs_last_error().decode())
         self.eigenvalues, self.residuals, self.eigenvectors = ev, rs, X
@@ -624,11 +680,12 @@ class MxSolver:
         self.seconds = sec.value
         return ev[: self.params.nev]
 
-    def check(self, div_op=None):
-        """checkEigensolution / checkDivergences (MxMagWaveOp.cpp:1118-1234)."""
+    def check(self, div_op=None, A=None):
+        """checkEigensolution / checkDivergences (MxMagWaveOp.cpp:1118-1234). A: operator of the residual check (the
+        reference uses curlCurl there, not the vector Laplacian it solves with); default = the solver's own operator."""
         m = self.params.block_size
         res, div = np.zeros(m), np.zeros(m)
-        rc = self._S.mxs_check_eigensolution(self.ctx.h, self.A.h, self.m_diag.h if self.m_diag is not None else None,
+        rc = self._S.mxs_check_eigensolution(self.ctx.h, (A if A is not None else self.A).h, self.m_diag.h if self.m_diag is not None else None,
                                              div_op.h if div_op is not None else None, self.eigenvectors.h,
                                              self.eigenvalues.ctypes.data, res.ctypes.data, div.ctypes.data)
         if rc != 0:
@@ -640,24 +697,41 @@ class MxMagWaveOp:
     """The shift-invert operator the reference hands to Anasazi (src/MxMagWaveOp.cpp:825-943):
     y = P (L - sigma M)^-1 M x, with the divergence-cleaning projection P. Inner solves: block PCG on the GPU."""
 
+    LIN_SOLVERS = {"cg": 0, "bicgstab": 1, "gmres": 2}   # "linear solver : type" (MxMagWaveOp.cpp:326-338)
+
     def __init__(self, ctx, vec_lapl, m_diag, div_b=None, grad_psi=None, sca_lapl=None, vec_prec=None, sca_prec=None,
-                 shift=0.0, lin_tol=1e-10):
+                 shift=0.0, lin_tol=1e-10, lin_solver="cg", lin_basis=20, max_lin_iters=1000):
         self._S = load_solver()
         self.ctx, self.L, self.m, self.D, self.G, self.S = ctx, vec_lapl, m_diag, div_b, grad_psi, sca_lapl
         self.vec_prec, self.sca_prec, self.shift, self.lin_tol = vec_prec, sca_prec, float(shift), float(lin_tol)
         self.has_curl_null = div_b is not None
+        self.lin_solver, self.lin_basis, self.max_lin_iters = self.LIN_SOLVERS[lin_solver], int(lin_basis), int(max_lin_iters)
         self.num_vec_lin_iters = self.num_sca_lin_iters = self.num_applies = 0
 
     def Apply(self, x, y):
         h = lambda o: o.h if o is not None else None
         info = (C.c_int64 * 2)()
-        rc = self._S.mxs_magwave_apply(self.ctx.h, self.L.h, self.m.h, h(self.D), h(self.G), h(self.S), h(self.vec_prec),
-                                       h(self.sca_prec), self.shift, self.lin_tol, int(self.has_curl_null), x.h, y.h, info)
+        rc = self._S.mxs_magwave_apply_ex(self.ctx.h, self.L.h, self.m.h, h(self.D), h(self.G), h(self.S), h(self.vec_prec),
+                                          h(self.sca_prec), self.shift, self.lin_tol, int(self.has_curl_null), self.lin_solver,
+                                          self.lin_basis, self.max_lin_iters, x.h, y.h, info)
         if rc != 0:
             raise MxError(self._S.mxs_last_error().decode())
         self.num_applies += 1
         self.num_vec_lin_iters += info[0]
         self.num_sca_lin_iters += info[1]
+
+
+def div_project(ctx, m_diag, X, divB, gradPsi, scaLapl, sca_prec=None, tol=1e-10, max_iters=500):
+    """X <- P X = X + gradPsi scaLapl^-1 divB M X (MxMagWaveOp.cpp:893-924); returns the inner CG iteration count."""
+    S = load_solver()
+    P = Projection()
+    P.divB, P.gradPsi, P.scaLapl = divB.h, gradPsi.h, scaLapl.h
+    P.sca_prec = sca_prec.h if sca_prec is not None else None
+    P.max_iters = int(max_iters)
+    info = (C.c_int64 * 1)()
+    if S.mxs_div_project(ctx.h, m_diag.h if m_diag is not None else None, C.byref(P), float(tol), X.h, info) != 0:
+        raise MxError(S.mxs_last_error().decode())
+    return int(info[0])
 
 
 def mag_to_elec(ctx, curl_b, inv_eps, mag, elec):

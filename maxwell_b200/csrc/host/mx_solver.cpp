@@ -8,7 +8,7 @@
 
 namespace {
 thread_local std::string g_err;
-thread_local double g_profile[4] = {0, 0, 0, 0};
+thread_local double g_profile[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 struct Wrapped {
   std::shared_ptr<MxComm> comm;
   std::shared_ptr<MxMap> map;
@@ -23,8 +23,8 @@ Wrapped wrap(mxg_ctx* ctx, mxg_mv* X) {
 // Scalar = double: real symmetric pencil; Scalar = MxComplex: Hermitian pencil of a Bloch-periodic simulation (complex
 // operator, complex multivectors, m_diag a complex one-column multivector with real entries).
 template <class Scalar>
-void runLobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, mxg_mv* X, const mxs_params* p, double* evals,
-               double* resnorms, int64_t info[4], double* seconds) {
+void runLobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, const mxs_projection* proj, mxg_mv* X, const mxs_params* p,
+               double* evals, double* resnorms, int64_t* info, int ninfo, double* seconds, double* violation) {
   Wrapped w = wrap(ctx, X);
   MxAnasaziMV<Scalar> Xmv(X, w.map, false);
   MxCrsOperator<Scalar> Aop(A);
@@ -42,13 +42,34 @@ void runLobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, mxg_mv* 
   sp.randomInit = p->random_init != 0;
   sp.profile = p->verbose >= 2;
   MxSolverT<MxAnasaziMV<Scalar>, Scalar> solver(&Aop, Mop.get(), Top.get(), sp);
+  std::unique_ptr<MxGeoMultigridPrec<Scalar>> Tsca;
+  std::unique_ptr<MxDivProjector<Scalar>> P;
+  if (proj) {
+    if (proj->sca_prec) Tsca.reset(new MxGeoMultigridPrec<Scalar>(proj->sca_prec, false));
+    P.reset(new MxDivProjector<Scalar>(proj->divB, proj->gradPsi, proj->scaLapl, m_diag, Tsca.get(), w.comm,
+                                       proj->tol_init > 0 ? proj->tol_init : 1e-10, proj->max_iters > 0 ? proj->max_iters : 500));
+    solver.setConstraint(P.get());
+  }
+  if (proj) {
+    MxSolverParams& q = solver.params();
+    if (proj->tol_init > 0) q.projTolInit = proj->tol_init;
+    if (proj->tol_w > 0) q.projTolW = proj->tol_w;
+    if (proj->tol_x > 0) q.projTolX = proj->tol_x;
+    if (proj->reproject_ratio > 0) q.reprojectRatio = proj->reproject_ratio;
+  }
   MxSolverResult r = solver.solve(Xmv);
   const int m = sp.blockSize;
   if (evals) std::memcpy(evals, r.eigenvalues.data(), sizeof(double) * m);
   if (resnorms) std::memcpy(resnorms, r.residuals.data(), sizeof(double) * m);
-  if (info) { info[0] = r.iterations; info[1] = r.converged; info[2] = r.applyA; info[3] = r.applyPrec; }
+  if (info) {
+    const int64_t all[8] = {r.iterations, r.converged, r.applyA, r.applyPrec, r.projections, r.reprojections,
+                            P ? int64_t(P->numLinIters) : 0, P ? int64_t(P->numApplies) : 0};
+    for (int i = 0; i < ninfo && i < 8; ++i) info[i] = all[i];
+  }
   if (seconds) *seconds = r.seconds;
-  g_profile[0] = r.tApplyA; g_profile[1] = r.tPrec; g_profile[2] = r.tGram; g_profile[3] = r.tUpdate;
+  if (violation)
+    for (int j = 0; j < m; ++j) violation[j] = j < int(r.violation.size()) ? r.violation[j] : 0.0;
+  g_profile[0] = r.tApplyA; g_profile[1] = r.tPrec; g_profile[2] = r.tGram; g_profile[3] = r.tUpdate; g_profile[4] = r.tProj;
 }
 
 template <class Scalar>
@@ -95,13 +116,28 @@ void mxs_default_params(mxs_params* p) {
 
 const char* mxs_last_error(void) { return g_err.c_str(); }
 void mxs_last_profile(double out[4]) { for (int i = 0; i < 4; ++i) out[i] = g_profile[i]; }
+void mxs_last_profile_ex(double out[8]) { for (int i = 0; i < 8; ++i) out[i] = g_profile[i]; }
 
 int mxs_lobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, mxg_mv* X, const mxs_params* p,
                double* evals, double* resnorms, int64_t info[4], double* seconds) {
   try {
     if (!ctx || !A || !X || !p) throw std::runtime_error("mxs_lobpcg: NULL argument");
-    if (mxg_mv_is_complex(X)) runLobpcg<MxComplex>(ctx, A, m_diag, prec, X, p, evals, resnorms, info, seconds);
-    else runLobpcg<double>(ctx, A, m_diag, prec, X, p, evals, resnorms, info, seconds);
+    if (mxg_mv_is_complex(X)) runLobpcg<MxComplex>(ctx, A, m_diag, prec, nullptr, X, p, evals, resnorms, info, 4, seconds, nullptr);
+    else runLobpcg<double>(ctx, A, m_diag, prec, nullptr, X, p, evals, resnorms, info, 4, seconds, nullptr);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+int mxs_lobpcg_projected(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, const mxs_projection* proj, mxg_mv* X,
+                         const mxs_params* p, double* evals, double* resnorms, double* violation, int64_t info[8], double* seconds) {
+  try {
+    if (!ctx || !A || !X || !p || !proj) throw std::runtime_error("mxs_lobpcg_projected: NULL argument");
+    if (!proj->divB || !proj->gradPsi || !proj->scaLapl) throw std::runtime_error("mxs_lobpcg_projected: projection operators missing");
+    if (mxg_mv_is_complex(X)) runLobpcg<MxComplex>(ctx, A, m_diag, prec, proj, X, p, evals, resnorms, info, 8, seconds, violation);
+    else runLobpcg<double>(ctx, A, m_diag, prec, proj, X, p, evals, resnorms, info, 8, seconds, violation);
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();
@@ -125,25 +161,67 @@ int mxs_check_eigensolution(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_crs* d
 }  // extern "C"
 
 // MxMagWaveOp::Apply (reference src/MxMagWaveOp.cpp:825-943): Y = P (L - sigma M)^-1 M X.
-// info[0] = vector-solve CG iterations, info[1] = scalar-solve CG iterations.
-extern "C" int mxs_magwave_apply(mxg_ctx* ctx, mxg_crs* vecLapl, mxg_mv* m_diag, mxg_crs* divB, mxg_crs* gradPsi, mxg_crs* scaLapl,
-                                 mxg_gmg* vecPrec, mxg_gmg* scaPrec, double shift, double linTol, int hasCurlNull,
-                                 mxg_mv* X, mxg_mv* Y, int64_t info[2]) {
+// info[0] = vector-solve Krylov iterations, info[1] = scalar-solve CG iterations.
+namespace {
+template <class Scalar>
+void runMagWave(mxg_ctx* ctx, mxg_crs* vecLapl, mxg_mv* m_diag, mxg_crs* divB, mxg_crs* gradPsi, mxg_crs* scaLapl, mxg_gmg* vecPrec,
+                mxg_gmg* scaPrec, double shift, double linTol, int hasCurlNull, int linSolver, int linBasis, int maxIters, mxg_mv* X,
+                mxg_mv* Y, int64_t info[2]) {
+  Wrapped w = wrap(ctx, X);
+  MxAnasaziMV<Scalar> Xmv(X, w.map, false), Ymv(Y, w.map, false);
+  std::unique_ptr<MxGeoMultigridPrec<Scalar>> Tv, Ts;
+  if (vecPrec) Tv.reset(new MxGeoMultigridPrec<Scalar>(vecPrec, false));
+  if (scaPrec) Ts.reset(new MxGeoMultigridPrec<Scalar>(scaPrec, false));
+  MxMagWaveOpParams p;
+  p.shift = shift;
+  p.linTol = linTol;
+  p.hasCurlNull = hasCurlNull != 0;
+  p.linSolver = linSolver == 1 ? mx::LIN_BICGSTAB : (linSolver == 2 ? mx::LIN_GMRES : mx::LIN_CG);
+  if (linBasis > 0) p.linBasis = linBasis;
+  if (maxIters > 0) p.maxLinIters = maxIters;
+  MxMagWaveOpT<Scalar> op(vecLapl, m_diag, divB, gradPsi, scaLapl, Tv.get(), Ts.get(), w.comm, p);
+  op.Apply(Xmv, Ymv);
+  if (info) { info[0] = op.numVecLinIters; info[1] = op.numScaLinIters(); }
+}
+}  // namespace
+
+extern "C" int mxs_magwave_apply_ex(mxg_ctx* ctx, mxg_crs* vecLapl, mxg_mv* m_diag, mxg_crs* divB, mxg_crs* gradPsi, mxg_crs* scaLapl,
+                                    mxg_gmg* vecPrec, mxg_gmg* scaPrec, double shift, double linTol, int hasCurlNull, int linSolver,
+                                    int linBasis, int maxIters, mxg_mv* X, mxg_mv* Y, int64_t info[2]) {
   try {
     if (!ctx || !vecLapl || !m_diag || !X || !Y) throw std::runtime_error("mxs_magwave_apply: NULL argument");
     if (hasCurlNull && (!divB || !gradPsi || !scaLapl)) throw std::runtime_error("mxs_magwave_apply: projection operators missing");
+    if (mxg_mv_is_complex(X))
+      runMagWave<MxComplex>(ctx, vecLapl, m_diag, divB, gradPsi, scaLapl, vecPrec, scaPrec, shift, linTol, hasCurlNull, linSolver, linBasis, maxIters, X, Y, info);
+    else
+      runMagWave<double>(ctx, vecLapl, m_diag, divB, gradPsi, scaLapl, vecPrec, scaPrec, shift, linTol, hasCurlNull, linSolver, linBasis, maxIters, X, Y, info);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+extern "C" int mxs_magwave_apply(mxg_ctx* ctx, mxg_crs* vecLapl, mxg_mv* m_diag, mxg_crs* divB, mxg_crs* gradPsi, mxg_crs* scaLapl,
+                                 mxg_gmg* vecPrec, mxg_gmg* scaPrec, double shift, double linTol, int hasCurlNull,
+                                 mxg_mv* X, mxg_mv* Y, int64_t info[2]) {
+  return mxs_magwave_apply_ex(ctx, vecLapl, m_diag, divB, gradPsi, scaLapl, vecPrec, scaPrec, shift, linTol, hasCurlNull, 0, 0, 0, X, Y, info);
+}
+
+// the projection alone: X <- P X = X + gradPsi scaLapl^-1 divB M X (src/MxMagWaveOp.cpp:893-924); info[0] = CG iterations
+extern "C" int mxs_div_project(mxg_ctx* ctx, mxg_mv* m_diag, const mxs_projection* proj, double tol, mxg_mv* X, int64_t info[1]) {
+  try {
+    if (!ctx || !proj || !X || !proj->divB || !proj->gradPsi || !proj->scaLapl) throw std::runtime_error("mxs_div_project: NULL argument");
     Wrapped w = wrap(ctx, X);
-    MxAnasaziMV<double> Xmv(X, w.map, false), Ymv(Y, w.map, false);
-    std::unique_ptr<MxGeoMultigridPrec<double>> Tv, Ts;
-    if (vecPrec) Tv.reset(new MxGeoMultigridPrec<double>(vecPrec, false));
-    if (scaPrec) Ts.reset(new MxGeoMultigridPrec<double>(scaPrec, false));
-    MxMagWaveOpParams p;
-    p.shift = shift;
-    p.linTol = linTol;
-    p.hasCurlNull = hasCurlNull != 0;
-    MxMagWaveOp op(vecLapl, m_diag, divB, gradPsi, scaLapl, Tv.get(), Ts.get(), p);
-    op.Apply(Xmv, Ymv);
-    if (info) { info[0] = op.numVecLinIters; info[1] = op.numScaLinIters; }
+    auto run = [&](auto tag) {
+      typedef decltype(tag) Scalar;
+      MxAnasaziMV<Scalar> Xmv(X, w.map, false);
+      std::unique_ptr<MxGeoMultigridPrec<Scalar>> Ts;
+      if (proj->sca_prec) Ts.reset(new MxGeoMultigridPrec<Scalar>(proj->sca_prec, false));
+      MxDivProjector<Scalar> P(proj->divB, proj->gradPsi, proj->scaLapl, m_diag, Ts.get(), w.comm, tol, proj->max_iters > 0 ? proj->max_iters : 500);
+      P.project(Xmv, tol);
+      if (info) info[0] = P.numLinIters;
+    };
+    if (mxg_mv_is_complex(X)) run(MxComplex()); else run(double());
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();
@@ -157,7 +235,7 @@ extern "C" int mxs_mag_to_elec(mxg_ctx* ctx, mxg_crs* curlB, mxg_crs* invEps, mx
     if (!ctx || !curlB || !mag || !elec) throw std::runtime_error("mxs_mag_to_elec: NULL argument");
     Wrapped wm = wrap(ctx, mag), we = wrap(ctx, elec);
     MxAnasaziMV<double> B(mag, wm.map, false), E(elec, we.map, false);
-    MxMagWaveOp::magToElec(curlB, invEps, B, E);
+    MxMagWaveOpT<double>::magToElec(curlB, invEps, B, E);
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();
@@ -171,7 +249,7 @@ extern "C" int mxs_eigvals_to_freqs(const double* re, const double* im, int n, d
     if (n < 0 || (n > 0 && (!re || !fre || !fim))) throw std::runtime_error("mxs_eigvals_to_freqs: bad argument");
     std::vector<std::complex<double>> ev(n), fr;
     for (int i = 0; i < n; ++i) ev[i] = std::complex<double>(re[i], im ? im[i] : 0.0);
-    MxMagWaveOp::eigValsToFreqs(ev, fr, shift, invert != 0);
+    MxMagWaveOpT<double>::eigValsToFreqs(ev, fr, shift, invert != 0);
     for (int i = 0; i < n; ++i) { fre[i] = fr[i].real(); fim[i] = fr[i].imag(); }
     return 0;
   } catch (const std::exception& e) {

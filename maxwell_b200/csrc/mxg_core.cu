@@ -40,6 +40,25 @@ int allReduceScratch(mxg_ctx* ctx, size_t count) {
   MXG_NCCL(ncclAllReduce(ctx->dScratch, ctx->dScratch, count, ncclDouble, ncclSum, ctx->comm, ctx->stream));
   return MXG_OK;
 }
+int mapGlobalCount(mxg_map* map, int64_t* out) {
+  if (map->nMapGlobal < 0) {
+    mxg_ctx* ctx = map->ctx;
+    int64_t cnt = map->nLocal;
+    if (ctx->nranks > 1) {
+      MXG_REQUIRE(ctx->comm != nullptr, "communicator not initialised");
+      int64_t* d = nullptr;
+      MXG_CUDA(cudaMalloc(&d, sizeof(int64_t)));
+      MXG_CUDA(cudaMemcpyAsync(d, &cnt, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+      MXG_NCCL(ncclAllReduce(d, d, 1, ncclInt64, ncclSum, ctx->comm, ctx->stream));
+      MXG_CUDA(cudaMemcpyAsync(&cnt, d, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+      MXG_CUDA(cudaStreamSynchronize(ctx->stream));
+      MXG_CUDA(cudaFree(d));
+    }
+    map->nMapGlobal = cnt;
+  }
+  *out = map->nMapGlobal;
+  return MXG_OK;
+}
 }  // namespace mxg
 
 MvStorage::~MvStorage() {

@@ -159,12 +159,18 @@ int vcycle(mxg_gmg* g, int l, mxg_mv* x, const mxg_mv* b, bool zeroStart) {
   // r = b - A x  (fused SpMM epilogue)
   rc = mxg_mv_assign(r, b);
   if (!rc) { g->spmmCount++; rc = mxg_crs_apply_axpby(g->A[l], mone, x, one, r); }
-  // coarsen
+  // coarsen (MxGeoMultigridPrec.cpp:447-452)
   if (!rc) { g->spmmCount++; rc = mxg_crs_apply(g->R[l], r, bc); }
+  if (!rc && p.remove_const_field) rc = mxg_mv_remove_const_field(bc);
   // coarse-grid correction from a zero initial guess
   if (!rc) rc = vcycle<T>(g, l + 1, xc, bc, true);
-  // x += P e
-  if (!rc) { g->spmmCount++; rc = mxg_crs_apply_axpby(g->P[l], one, xc, one, x); }
+  // x += P e (refine, :438-443); with "remove const field" the refined correction is cleaned before it is added
+  if (!rc && p.remove_const_field) {
+    g->spmmCount++;
+    rc = mxg_crs_apply(g->P[l], xc, r);
+    if (!rc) rc = mxg_mv_remove_const_field(r);
+    if (!rc) rc = mxg_mv_add_mv(x, one, x, one, r);
+  } else if (!rc) { g->spmmCount++; rc = mxg_crs_apply_axpby(g->P[l], one, xc, one, x); }
   if (!rc) rc = smooth<T>(g, l, x, b, p.smoother_degree, p.eig_ratio, false);
   mxg_mv_destroy(r);
   mxg_mv_destroy(bc);
@@ -242,12 +248,14 @@ int applyImpl(mxg_gmg* g, const mxg_mv* b, mxg_mv* x) {
     if ((rc = viewCols(g->x[l], nc, &xl[l]))) break;
     g->spmmCount++;
     rc = mxg_crs_apply(g->R[l - 1], bl[l - 1], bl[l]);
+    if (!rc && p.remove_const_field) rc = mxg_mv_remove_const_field(bl[l]);
   }
   const int last = g->nlevels - 1;
   if (!rc) rc = smooth<T>(g, last, xl[last], bl[last], p.coarse_degree, p.coarse_eig_ratio, true);
   for (int l = last - 1; l >= 0 && !rc; --l) {
     g->spmmCount++;
     rc = mxg_crs_apply(g->P[l], xl[l + 1], xl[l]);
+    if (!rc && p.remove_const_field) rc = mxg_mv_remove_const_field(xl[l]);
     // the coarse work vectors b[l+1], x[l+1] are reused inside vcycle(l): stash what is still needed
     // (nothing: levels below l are finished once their solution has been interpolated up)
     for (int c = 0; c < p.cycles && !rc; ++c) rc = vcycle<T>(g, l, xl[l], bl[l], false);
@@ -273,12 +281,14 @@ void mxg_gmg_default_params(mxg_gmg_params* p) {
   p->coarse_eig_ratio = 1000.0;
   p->full_multigrid = 0;
   p->power_iterations = 30;
+  p->remove_const_field = 0;   // "linear solver : remove const field" default (MxGeoMultigridPrec.cpp:108)
 }
 
 int mxg_gmg_create(mxg_ctx* ctx, int nlevels, mxg_crs* const* ops, mxg_crs* const* restrictors, mxg_crs* const* prolongators,
                    const mxg_gmg_params* params, mxg_gmg** out) {
   MXG_REQUIRE(ctx && ops && out && nlevels >= 1, "mxg_gmg_create: bad argument");
   MXG_REQUIRE(nlevels == 1 || (restrictors && prolongators), "mxg_gmg_create: transfer operators missing");
+  MXG_REQUIRE(ops[0] != nullptr, "mxg_gmg_create: level 0 operator is NULL");
   mxg_gmg* g = new mxg_gmg;
   g->ctx = ctx;
   g->nlevels = nlevels;
@@ -335,6 +345,8 @@ int mxg_gmg_apply(mxg_gmg* g, const mxg_mv* b, mxg_mv* x) {
   MXG_REQUIRE(b->ld == g->A[0]->nRows && x->ld == g->A[0]->nRows, "mxg_gmg_apply: vector length does not match the fine level");
   MXG_REQUIRE(b->ncols == x->ncols, "mxg_gmg_apply: column counts differ");
   MXG_REQUIRE(b->isComplex == g->isComplex && x->isComplex == g->isComplex, "mxg_gmg_apply: mixed real/complex operands");
+  for (void* pb : b->col)
+    for (void* px : x->col) MXG_REQUIRE(pb != px, "mxg_gmg_apply: x and b must not alias");
   MXG_CUDA(cudaSetDevice(g->ctx->device));
   return g->isComplex ? applyImpl<zd>(g, b, x) : applyImpl<double>(g, b, x);
 }

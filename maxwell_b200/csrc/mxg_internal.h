@@ -107,7 +107,8 @@ struct mxg_ctx {
 
 struct mxg_map {
   mxg_ctx* ctx = nullptr;
-  int64_t nGlobal = 0, nLocal = 0;
+  int64_t nGlobal = 0, nLocal = 0;      // size of the GID space / DOFs owned by this rank
+  int64_t nMapGlobal = -1;             // DOFs in the map over all ranks (lazily all-reduced: mxg::mapGlobalCount)
   std::vector<int64_t> gids;           // host copy (ascending)
   int64_t* dGids = nullptr;            // device copy (RNG keys, halo plans); in DEVICE order when the map is ordered
   // Optional component-major device ordering (mxg_map_create_ordered): perm[device position] = reference local index,
@@ -219,6 +220,8 @@ int ensureScratch(mxg_ctx* ctx, size_t bytes);
 int ensurePinned(mxg_ctx* ctx, size_t bytes);
 // sum `count` doubles in ctx->dScratch over all ranks (no-op on one rank)
 int allReduceScratch(mxg_ctx* ctx, size_t count);
+// number of DOFs of the map over all ranks (collective on first use when the context has several ranks)
+int mapGlobalCount(mxg_map* map, int64_t* out);
 inline int gridFor(const mxg_ctx* ctx, int64_t work, int block, int perSM) {
   int64_t need = (work + block - 1) / block;
   int64_t cap = int64_t(ctx->numSMs) * perSM;

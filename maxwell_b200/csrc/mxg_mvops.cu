@@ -132,6 +132,47 @@ __global__ void __launch_bounds__(kBlock) k_reduce_partials(const T* __restrict_
   if (threadIdx.x == 0) out[blockIdx.x] = r;
 }
 
+// dst_j = a_j * A_j + b_j * B_j with one scalar pair per column (the CG / Chebyshev recurrences: x += alpha_j p,
+// r -= alpha_j q, p = z + beta_j p in ONE kernel each instead of copy + MvScale(vector) + MvAddMv). A or B may alias dst.
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_axpby_cols(ColTable<T> d, ScalarList<T> a, ColTable<T> A, ScalarList<T> b, ColTable<T> B, int64_t n) {
+  T* dst = d.p[blockIdx.y];
+  const T* pa = A.p[blockIdx.y];
+  const T* pb = B.p[blockIdx.y];
+  const T sa = a.v[blockIdx.y], sb = b.v[blockIdx.y];
+  for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) dst[i] = sa * pa[i] + sb * pb[i];
+}
+
+// partial[col * gridDim.x + block] = sum over this block's rows of a
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_sum_partial(ColTable<T> A, int64_t n, T* __restrict__ partial) {
+  __shared__ T sm[kBlock / 32];
+  const T* __restrict__ a = A.p[blockIdx.y];
+  T acc = zeroOf<T>();
+  for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) acc += a[i];
+  T r = blockSum(acc, sm);
+  if (threadIdx.x == 0) partial[blockIdx.y * int64_t(gridDim.x) + blockIdx.x] = r;
+}
+// x_j -= sums[j] / count (sums stay on the device: no host round trip between the reduction and the update)
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_sub_mean(ColTable<T> X, const T* __restrict__ sums, double invCount, int64_t n) {
+  T* __restrict__ x = X.p[blockIdx.y];
+  const T s = sums[blockIdx.y];
+  for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) {
+    T v = x[i];
+    if constexpr (sizeof(T) == sizeof(double)) v = v - s * invCount;
+    else { v.x -= s.x * invCount; v.y -= s.y * invCount; }
+    x[i] = v;
+  }
+}
+// x_j[i] = 0 where frac[i] == 0 (MxGridField::zeroUnusedComponents)
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_zero_unused(ColTable<T> X, const double* __restrict__ frac, int fracStride, int64_t n) {
+  T* __restrict__ x = X.p[blockIdx.y];
+  for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock)
+    if (frac[i * fracStride] == 0.0) x[i] = zeroOf<T>();
+}
+
 // ---- tall-skinny Gram product: C(k x b) = A^H X ---------------------------------------------
 // Each thread owns a KT x BT register tile of C and streams rows with stride kBlock (coalesced
 // per column). blockIdx.x enumerates tiles (fastest), blockIdx.y row slices: blocks that share
@@ -475,6 +516,32 @@ int timesMatImpl(const double alpha[2], const mxg_mv* A, const double* B, int ld
   return MXG_OK;
 }
 
+template <class T>
+int removeConstImpl(mxg_mv* mv, int64_t count) {
+  mxg_ctx* ctx = mv->map->ctx;
+  const int nc = mv->ncols;
+  constexpr int w = sizeof(T) / sizeof(double);
+  int np = gridFor(ctx, mv->ld, kBlock * 8, 4);
+  int cap = (ctx->numSMs * 4 + nc - 1) / nc;
+  if (np > cap) np = cap;
+  if (np < 1) np = 1;
+  int rc = ensureScratch(ctx, sizeof(T) * (size_t(nc) * np + nc));
+  if (rc) return rc;
+  T* out = reinterpret_cast<T*>(ctx->dScratch);
+  T* partial = out + nc;
+  k_sum_partial<T><<<dim3(np, nc), kBlock, 0, ctx->stream>>>(tableOf<T>(mv), mv->ld, partial);
+  LAUNCH_CHECK(ctx);
+  k_reduce_partials<T><<<nc, kBlock, 0, ctx->stream>>>(partial, np, out);
+  LAUNCH_CHECK(ctx);
+  rc = allReduceScratch(ctx, size_t(nc) * w);
+  if (rc) return rc;
+  if (mv->ld > 0) {
+    k_sub_mean<T><<<gridCols<T>(ctx, mv->ld, nc), kBlock, 0, ctx->stream>>>(tableOf<T>(mv), out, 1.0 / double(count), mv->ld);
+    LAUNCH_CHECK(ctx);
+  }
+  return MXG_OK;
+}
+
 bool overlaps(const mxg_mv* a, const mxg_mv* b) {
   if (a->storage.get() != b->storage.get()) return false;
   for (void* pa : a->col)
@@ -559,6 +626,58 @@ int mxg_mv_add_mv(mxg_mv* dst, const double alpha[2], const mxg_mv* A, const dou
   MXG_REQUIRE(alpha && beta, "mxg_mv_add_mv: NULL scalar");
   MXG_CUDA(cudaSetDevice(dst->map->ctx->device));
   return dst->isComplex ? axpbyImpl<zd>(dst, alpha, A, beta, B) : axpbyImpl<double>(dst, alpha, A, beta, B);
+}
+
+// dst_j = alphas[j] * A_j + betas[j] * B_j: MvAddMv (MxAnasaziMV.cpp:89-111) with per-column scalars as in
+// MvScale(vector) (MxAnasaziMV.hpp:110-118); A and/or B may alias dst.
+int mxg_mv_axpby_cols(mxg_mv* dst, const double* alphas, const mxg_mv* A, const double* betas, const mxg_mv* B) {
+  int rc = checkSame("mxg_mv_axpby_cols", dst, A);
+  if (rc) return rc;
+  rc = checkSame("mxg_mv_axpby_cols", dst, B);
+  if (rc) return rc;
+  MXG_REQUIRE(alphas && betas, "mxg_mv_axpby_cols: NULL scalar list");
+  if (dst->ld == 0) return MXG_OK;
+  mxg_ctx* ctx = dst->map->ctx;
+  MXG_CUDA(cudaSetDevice(ctx->device));
+  if (dst->isComplex) {
+    ScalarList<zd> a, b;
+    for (int j = 0; j < dst->ncols; ++j) { a.v[j] = {alphas[2 * j], alphas[2 * j + 1]}; b.v[j] = {betas[2 * j], betas[2 * j + 1]}; }
+    k_axpby_cols<zd><<<gridCols<zd>(ctx, dst->ld, dst->ncols), kBlock, 0, ctx->stream>>>(tableOf<zd>(dst), a, tableOf<zd>(A), b, tableOf<zd>(B), dst->ld);
+  } else {
+    ScalarList<double> a, b;
+    for (int j = 0; j < dst->ncols; ++j) { a.v[j] = alphas[j]; b.v[j] = betas[j]; }
+    k_axpby_cols<double><<<gridCols<double>(ctx, dst->ld, dst->ncols), kBlock, 0, ctx->stream>>>(tableOf<double>(dst), a, tableOf<double>(A), b, tableOf<double>(B), dst->ld);
+  }
+  LAUNCH_CHECK(ctx);
+  return MXG_OK;
+}
+
+// removeConstField (MxGeoMultigridPrec.cpp:400-411, MxUtil.cpp:483-503): x_j -= (x_j . 1) / (1 . 1) 1, column by column;
+// reduction, all-reduce and update are enqueued back to back, the sums never visit the host.
+int mxg_mv_remove_const_field(mxg_mv* mv) {
+  MXG_REQUIRE(mv, "mxg_mv_remove_const_field: NULL argument");
+  MXG_CUDA(cudaSetDevice(mv->map->ctx->device));
+  int64_t cnt = 0;
+  int rc = mapGlobalCount(mv->map, &cnt);
+  if (rc) return rc;
+  MXG_REQUIRE(cnt > 0, "mxg_mv_remove_const_field: empty map");
+  return mv->isComplex ? removeConstImpl<zd>(mv, cnt) : removeConstImpl<double>(mv, cnt);
+}
+
+// MxGridField::zeroUnusedComponents (MxGridField.cpp:548-576, called on the initial block at MxSolver.cpp:65): zero the
+// entries whose shape fraction is 0. fracs: one-column multivector on the same map holding the fractions (real part used).
+int mxg_mv_zero_unused(mxg_mv* mv, const mxg_mv* fracs) {
+  MXG_REQUIRE(mv && fracs, "mxg_mv_zero_unused: NULL argument");
+  MXG_REQUIRE(fracs->ncols >= 1 && fracs->ld == mv->ld && fracs->map->ctx == mv->map->ctx, "mxg_mv_zero_unused: fraction vector does not match");
+  if (mv->ld == 0) return MXG_OK;
+  mxg_ctx* ctx = mv->map->ctx;
+  MXG_CUDA(cudaSetDevice(ctx->device));
+  const double* f = static_cast<const double*>(fracs->col[0]);
+  const int fs = fracs->isComplex ? 2 : 1;
+  if (mv->isComplex) k_zero_unused<zd><<<gridCols<zd>(ctx, mv->ld, mv->ncols), kBlock, 0, ctx->stream>>>(tableOf<zd>(mv), f, fs, mv->ld);
+  else k_zero_unused<double><<<gridCols<double>(ctx, mv->ld, mv->ncols), kBlock, 0, ctx->stream>>>(tableOf<double>(mv), f, fs, mv->ld);
+  LAUNCH_CHECK(ctx);
+  return MXG_OK;
 }
 
 int mxg_mv_update(mxg_mv* dst, const double a[2], const mxg_mv* A, const double s[2]) {

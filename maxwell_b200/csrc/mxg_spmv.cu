@@ -43,10 +43,10 @@ struct __align__(16) PatEntry<double> {
   int32_t pad;
 };
 template <>
-struct __align__(8) PatEntry<zd> {
+struct __align__(16) PatEntry<zd> {
   double vx, vy;
   int32_t d;
-  int32_t pad;
+  int32_t pad[3];
 };
 
 using Peer = mxg::HaloPeer;
@@ -217,11 +217,14 @@ __global__ void __launch_bounds__(kBlockIlv) k_spmm_dict_ilv3(int64_t rowBegin, 
 
 // ---- windowed dictionary kernel (design notes: mxg_spmm_win.cuh) ------------------------------------------------------
 // One CTA per tile of R = kWinThreads * RPT consecutive rows. Thread 0 arms an mbarrier and issues <= 3 bulk copies that
-// bring the tile's x windows into shared memory; meanwhile every thread fetches the pattern ids of its rows. For a block of
-// vectors the windows of vector j+1 are loaded into the second buffer while vector j is being consumed.
+// bring the tile's x windows into shared memory; meanwhile every warp fetches the pattern ids of its rows and stages the
+// pattern ENTRIES in a per-warp shared slot (the shared-memory carve-out leaves little L1, and a dependent global load per
+// entry made the first version of this kernel latency-bound: ncu, profiles/README_r02.md). The inner loop then touches
+// shared memory only: one broadcast 16-byte load per entry (value + offset) and one 8-byte gather per lane.
 // ILV = 3: warp w of a 384-row sub-tile takes rows 3*lane + (w mod 3) of its 96-row group -- 32 consecutive cells of ONE
-// field component, which share a pattern (one broadcast load per entry) and read shared memory with stride 3 (no bank
-// conflict). ILV = 1: lane = consecutive row (scalar fields).
+// field component, which share a pattern and read the window with stride 3 (no bank conflict). ILV = 1: lane = row.
+// A block of vectors is processed column by column through the same window buffer; several resident CTAs per SM overlap
+// one tile's copy with another's arithmetic.
 template <class T>
 __device__ __forceinline__ void winIssue(const WinTile& W, const T* __restrict__ xcol, T* buf, uint64_t* bar) {
   uint32_t bytes = 0;
@@ -236,14 +239,53 @@ __device__ __forceinline__ void winIssue(const WinTile& W, const T* __restrict__
   }
 }
 
+constexpr int kWinSlot = 16;   // pattern entries a per-warp slot holds (longer / non-uniform rows read the table directly)
+
+template <class T>
+__device__ __forceinline__ PatEntry<T> ldEntry(const PatEntry<T>* p) {
+  // one (two for complex) 16-byte load instead of separate value / offset loads
+  PatEntry<T> e;
+  const int4* s = reinterpret_cast<const int4*>(p);
+  int4* d = reinterpret_cast<int4*>(&e);
+#pragma unroll
+  for (int i = 0; i < int(sizeof(PatEntry<T>) / 16); ++i) d[i] = s[i];
+  return e;
+}
+
+struct WinShift {
+  int32_t dLo, dHi, s0, s1, s2;
+};
+// one row: entries from `ent` (per-warp shared slot or the global pattern table), x from the shared windows; ascending
+// column order with separately rounded multiply and add, as everywhere in this file
+template <class T>
+__device__ __forceinline__ T winRowDot(const PatEntry<T>* __restrict__ ent, int32_t len, int32_t r, const T* __restrict__ xs, const WinShift& w) {
+  T acc = zeroOf<T>();
+  int32_t q = 0;
+  for (; q + 1 < len; q += 2) {
+    const PatEntry<T> e0 = ldEntry<T>(ent + q);
+    const PatEntry<T> e1 = ldEntry<T>(ent + q + 1);
+    const T x0 = xs[r + e0.d + (e0.d < w.dLo ? w.s0 : (e0.d > w.dHi ? w.s2 : w.s1))];
+    const T x1 = xs[r + e1.d + (e1.d < w.dLo ? w.s0 : (e1.d > w.dHi ? w.s2 : w.s1))];
+    accum(acc, entryVal(e0), x0);
+    accum(acc, entryVal(e1), x1);
+  }
+  if (q < len) {
+    const PatEntry<T> e0 = ldEntry<T>(ent + q);
+    accum(acc, entryVal(e0), xs[r + e0.d + (e0.d < w.dLo ? w.s0 : (e0.d > w.dHi ? w.s2 : w.s1))]);
+  }
+  return acc;
+}
+
 template <class T, int ILV, int RPT>
 __global__ void __launch_bounds__(kWinThreads) k_spmm_win(int64_t rowBegin, int64_t rowEnd, int64_t tile0, DictArgs<T> D,
-                                                          const WinTile* __restrict__ tiles, int bufElems, int nbuf, XSource<T> X,
-                                                          ColTable<T> Y, int nvec, Epilogue<T> ep) {
+                                                          const WinTile* __restrict__ tiles, XSource<T> X, ColTable<T> Y, int nvec,
+                                                          Epilogue<T> ep) {
   extern __shared__ __align__(128) unsigned char smemRaw[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smemRaw);          // two barriers
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smemRaw);
   WinTile* Ws = reinterpret_cast<WinTile*>(smemRaw + 64);
-  T* buf = reinterpret_cast<T*>(smemRaw + 128);
+  PatEntry<T>* slots = reinterpret_cast<PatEntry<T>*>(smemRaw + 128);
+  constexpr int kWarps = kWinThreads / 32;
+  T* buf = reinterpret_cast<T*>(smemRaw + 128 + sizeof(PatEntry<T>) * kWarps * RPT * kWinSlot);
   constexpr int R = kWinThreads * RPT;
   const int64_t tile = tile0 + blockIdx.x;
   if (threadIdx.x == 0) {
@@ -251,23 +293,29 @@ __global__ void __launch_bounds__(kWinThreads) k_spmm_win(int64_t rowBegin, int6
     int4* dst = reinterpret_cast<int4*>(Ws);
 #pragma unroll
     for (int i = 0; i < 4; ++i) dst[i] = __ldg(src + i);
-    mbarInit(&bar[0], 1);
-    mbarInit(&bar[1], 1);
+    mbarInit(bar, 1);
     mbarFenceInit();
-    if (Ws->valid) winIssue<T>(*Ws, X.x.p[0], buf, &bar[0]);
+    if (Ws->valid) winIssue<T>(*Ws, X.x.p[0], buf, bar);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tOff = ILV == 3 ? (warp / 3) * 96 + 3 * lane + (warp % 3) : int(threadIdx.x);
   int64_t row[RPT];
-  int32_t o[RPT], oe[RPT];
+  int32_t o[RPT], len[RPT];
+  bool uni[RPT];
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
     row[i] = tile * R + i * kWinThreads + tOff;
-    o[i] = oe[i] = 0;
-    if (row[i] >= rowBegin && row[i] < rowEnd) {
-      const int32_t p = D.rowPat[row[i]];
-      if (p >= 0) { o[i] = __ldg(D.patOff + p); oe[i] = __ldg(D.patOff + p + 1); }
-    }
+    int32_t p = -1;
+    if (row[i] >= rowBegin && row[i] < rowEnd) p = D.rowPat[row[i]];
+    o[i] = len[i] = 0;
+    if (p >= 0) { o[i] = __ldg(D.patOff + p); len[i] = __ldg(D.patOff + p + 1) - o[i]; }
+    // warp-uniform pattern (lanes without a dictionary row do not count): stage its entries once for the whole warp
+    const int32_t pmax = __reduce_max_sync(0xffffffffu, p);
+    uni[i] = __all_sync(0xffffffffu, p < 0 || p == pmax) && pmax >= 0;
+    const int32_t oU = __shfl_sync(0xffffffffu, o[i], __ffs(__ballot_sync(0xffffffffu, p == pmax)) - 1);
+    const int32_t lenU = __shfl_sync(0xffffffffu, len[i], __ffs(__ballot_sync(0xffffffffu, p == pmax)) - 1);
+    uni[i] = uni[i] && lenU <= kWinSlot;
+    if (uni[i] && lane < lenU) slots[(warp * RPT + i) * kWinSlot + lane] = ldEntry<T>(D.pat + oU + lane);
   }
   __syncthreads();
   if (!Ws->valid) {   // tile-uniform: gather path
@@ -278,33 +326,20 @@ __global__ void __launch_bounds__(kWinThreads) k_spmm_win(int64_t rowBegin, int6
   }
   const int32_t dLo = Ws->dLo, dHi = Ws->dHi, s0 = Ws->shift[0], s1 = Ws->shift[1], s2 = Ws->shift[2];
   for (int j = 0; j < nvec; ++j) {
-    const int b = nbuf == 2 ? (j & 1) : 0;
-    if (nbuf == 2 && j + 1 < nvec && threadIdx.x == 0) winIssue<T>(*Ws, X.x.p[j + 1], buf + ((j + 1) & 1) * bufElems, &bar[(j + 1) & 1]);
-    mbarWait(&bar[b], nbuf == 2 ? ((j >> 1) & 1) : (j & 1));
-    const T* __restrict__ xs = buf + b * bufElems;
+    mbarWait(bar, j & 1);
+    const T* __restrict__ xs = buf;
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
-      if (oe[i] == o[i]) continue;
+      if (len[i] == 0) continue;
       const int32_t r = int32_t(row[i]);
-      T acc = zeroOf<T>();
-      int32_t q = o[i];
-      for (; q + 1 < oe[i]; q += 2) {
-        const PatEntry<T> e0 = D.pat[q];
-        const PatEntry<T> e1 = D.pat[q + 1];
-        const T x0 = xs[r + e0.d + (e0.d < dLo ? s0 : (e0.d > dHi ? s2 : s1))];
-        const T x1 = xs[r + e1.d + (e1.d < dLo ? s0 : (e1.d > dHi ? s2 : s1))];
-        accum(acc, entryVal(e0), x0);
-        accum(acc, entryVal(e1), x1);
-      }
-      if (q < oe[i]) {
-        const PatEntry<T> e0 = D.pat[q];
-        accum(acc, entryVal(e0), xs[r + e0.d + (e0.d < dLo ? s0 : (e0.d > dHi ? s2 : s1))]);
-      }
+      const WinShift ws{dLo, dHi, s0, s1, s2};
+      const T acc = uni[i] ? winRowDot<T>(slots + (warp * RPT + i) * kWinSlot, len[i], r, xs, ws)
+                           : winRowDot<T>(D.pat + o[i], len[i], r, xs, ws);
       storeY(Y.p[j], row[i], acc, ep);
     }
     if (j + 1 < nvec) {
-      __syncthreads();   // everyone is done with this buffer
-      if (nbuf == 1 && threadIdx.x == 0) winIssue<T>(*Ws, X.x.p[j + 1], buf, &bar[0]);
+      __syncthreads();   // everyone is done with the windows of vector j
+      if (threadIdx.x == 0) winIssue<T>(*Ws, X.x.p[j + 1], buf, bar);
     }
   }
 }
@@ -402,11 +437,12 @@ int launchSegments(const mxg_crs* A, const int64_t b[4], const int64_t e[4], con
 
 // rows per thread of the windowed kernel (tile = kWinThreads * RPT rows)
 template <class T> struct WinCfg;
-template <> struct WinCfg<double> { static constexpr int RPT = 4; };
-template <> struct WinCfg<zd> { static constexpr int RPT = 2; };
-constexpr size_t kWinSmemHeader = 128;
-constexpr size_t kWinSmemMax = 200 * 1024;      // per CTA, both buffers
+template <> struct WinCfg<double> { static constexpr int RPT = 2; };
+template <> struct WinCfg<zd> { static constexpr int RPT = 1; };
+constexpr size_t kWinSmemMax = 200 * 1024;      // per CTA
 constexpr size_t kWinBufBudget = 100 * 1024;    // one window set
+template <class T>
+constexpr size_t winSmemHeader() { return 128 + sizeof(PatEntry<T>) * (kWinThreads / 32) * WinCfg<T>::RPT * kWinSlot; }
 
 template <class T>
 int launchWin(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, const XSource<T>& X, const ColTable<T>& Y, int nvec,
@@ -415,20 +451,18 @@ int launchWin(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, const XSource<
   constexpr int RPT = WinCfg<T>::RPT;
   const int R = A->winR;
   const int64_t tile0 = rowBegin / R, tiles = (rowEnd + R - 1) / R - tile0;
-  const size_t bufBytes = size_t(A->winBufElems) * sizeof(T);
-  const int nbuf = (nvec > 1 && kWinSmemHeader + 2 * bufBytes <= kWinSmemMax) ? 2 : 1;
-  const size_t smem = kWinSmemHeader + nbuf * bufBytes;
+  const size_t smem = winSmemHeader<T>() + size_t(A->winBufElems) * sizeof(T);
   const DictArgs<T> D = dictArgs<T>(A);
   const WinTile* wt = static_cast<const WinTile*>(A->dWinTiles);
   static bool attrSet[2] = {false, false};
   if (A->winIlv == 3) {
     auto kern = k_spmm_win<T, 3, RPT>;
     if (!attrSet[0]) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWinSmemMax))); attrSet[0] = true; }
-    kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, D, wt, int(A->winBufElems), nbuf, X, Y, nvec, ep);
+    kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, D, wt, X, Y, nvec, ep);
   } else {
     auto kern = k_spmm_win<T, 1, RPT>;
     if (!attrSet[1]) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWinSmemMax))); attrSet[1] = true; }
-    kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, D, wt, int(A->winBufElems), nbuf, X, Y, nvec, ep);
+    kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, D, wt, X, Y, nvec, ep);
   }
   LAUNCH_CHECK(ctx);
   return MXG_OK;
@@ -1094,7 +1128,7 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
       const PatEntry<T>* pe = pat.data();
       int64_t maxTotal = 0, valid = 0;
       std::vector<WinTile> tiles = planWinTiles(rowPat.data(), patOff.data(), A->numPats, [pe](int32_t q) { return int64_t(pe[q].d); }, nRows,
-                                                nLoc, R, align, int64_t(kWinBufBudget / sizeof(T)), &maxTotal, &valid);
+                                                nLoc, R, align, int64_t(std::min(kWinBufBudget, kWinSmemMax - winSmemHeader<T>()) / sizeof(T)), &maxTotal, &valid);
       if (valid > 0) {
         WinTile* dT = nullptr;
         if ((rc = uploadVec(tiles, &dT, &A->deviceBytes, ctx))) return rc;

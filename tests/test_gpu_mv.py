@@ -214,3 +214,32 @@ def _dense(gids, vals, lo, hi):
     out = np.zeros(hi - lo, dtype=vals.dtype)
     out[gids - lo] = vals
     return out
+
+
+def test_axpby_cols_remove_const_zero_unused(mx, ctx):
+    """Per-column fused update (the CG / Chebyshev recurrences), removeConstField (MxGeoMultigridPrec.cpp:400-411,
+    MxUtil.cpp:483-503) and MxGridField::zeroUnusedComponents (MxGridField.cpp:548-576)."""
+    n = 10007
+    m = mx.MxMap(ctx, n, np.arange(n, dtype=np.int64))
+    for cx in (False, True):
+        A, B, Dst = (mx.MxMultiVector(m, 3, cx) for _ in range(3))
+        A.random(1)
+        B.random(2)
+        a, b = A.to_host(), B.to_host()
+        al = np.array([0.5, -2.0, 0.0]) + (1j * np.array([0.25, 0.0, 1.0]) if cx else 0)
+        be = np.array([1.0, 3.0, -1.5]) + (1j * np.array([0.0, -0.5, 2.0]) if cx else 0)
+        Dst.axpby_cols(al, A, be, B)
+        np.testing.assert_allclose(Dst.to_host(), a * al[None, :] + b * be[None, :], rtol=1e-14, atol=1e-14)
+        A.axpby_cols(al, A, be, B)                      # aliasing dst = A
+        np.testing.assert_allclose(A.to_host(), a * al[None, :] + b * be[None, :], rtol=1e-14, atol=1e-14)
+        B.remove_const_field()
+        got = B.to_host()
+        np.testing.assert_allclose(got, b - b.mean(axis=0)[None, :], rtol=1e-12, atol=1e-13)
+        assert np.abs(got.sum(axis=0)).max() < 1e-9
+        f = mx.MxMultiVector(m, 1, cx)
+        frac = (np.arange(n) % 3 != 0).astype(np.float64) * 0.7
+        f.from_host(frac.astype(np.complex128) if cx else frac)
+        before = Dst.to_host()
+        Dst.zero_unused(f)
+        after = Dst.to_host()
+        assert np.all(after[frac == 0] == 0) and np.array_equal(after[frac != 0], before[frac != 0])

@@ -105,14 +105,10 @@ def test_pillbox_eigenvalues_match_scipy(mx, ctx, orc, use_prec):
     assert abs(maxwell[0] - (2.405 / 0.4) ** 2) < 0.8
 
 
-@pytest.mark.xfail(strict=False, reason="complex instantiation of the driver is validated on the host multivector "
-                                        "(tests/cpp/solver_host_check.cpp); its first GPU run was still pending when the "
-                                        "round's GPU budget ran out")
 def test_complex_bloch_eigensolve_matches_analytic_spectrum():
     """Hermitian instantiation of the driver (MxSolverT<MxAnasaziMV<complex>, complex>) on the Bloch-periodic vacuum
     vector Laplacian (the pencil operator of config C4's class): eigenvalues sum_i (2/h sin((2 pi m_i + phi_i) / (2 N)))^2,
-    three times each (one per field component). Runs in its own process (tests/complex_solve_check.py) so that a fault
-    in this not-yet-exercised path cannot disturb the CUDA context of the other tests."""
+    three times each (one per field component). Runs in its own process (tests/complex_solve_check.py)."""
     import os
     import subprocess
     import sys
@@ -120,3 +116,47 @@ def test_complex_bloch_eigensolve_matches_analytic_spectrum():
     res = subprocess.run([sys.executable, os.path.join(root, "tests", "complex_solve_check.py")], capture_output=True, text=True,
                          timeout=300)
     assert res.returncode == 0 and "COMPLEX SOLVE OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_full_multigrid_is_the_spec_apply_inverse(mx, ctx, orc):
+    """MxGeoMultigridPrec::ApplyInverse is fullVCycle (MxGeoMultigridPrec.cpp:496-616): restrict b to every level, solve the
+    coarsest, interpolate up with `cycles` V-cycles per level. As a one-shot solver it must beat a single V-cycle from zero."""
+    sims, ops, maps, R, P = _hierarchy(mx, ctx, orc, orc.pillbox, [32, 16, 8])
+    op = sims[0].op("vecLapl")
+    fa = sims[0].fracs("bfield")
+    rng = np.random.default_rng(1)
+    xs = rng.standard_normal((op.nrows, 3)) * (fa > 0)[:, None]
+    bh = op.apply(xs)
+    b = mx.MxMultiVector(maps[0], 3)
+    b.from_host(bh)
+    res = {}
+    for fmg in (False, True):
+        prec = mx.MxGeoMultigridPrec(ctx, ops, R, P, smoother_sweeps=2, cycles=1, full_multigrid=fmg)
+        x = mx.MxMultiVector(maps[0], 3)
+        prec.ApplyInverse(b, x)
+        r = b.CloneCopy()
+        ops[0].apply_axpby(-1.0, x, 1.0, r)
+        res[fmg] = r.norm2() / b.norm2()
+        assert np.all(np.isfinite(res[fmg]))
+    assert np.all(res[True] < 0.7), res
+    assert np.all(res[True] < res[False] * 1.05), res
+
+
+def test_complex_multigrid_on_bloch_periodic_levels(mx, ctx, orc):
+    """The V-cycle on complex (Bloch-periodic) level operators: contraction of the stationary iteration."""
+    ph = (0.7, -0.4, 1.1)
+    sims, ops, maps, R, P = _hierarchy(mx, ctx, orc, lambda n: orc.vacuum(n, phase_shifts=ph), [16, 8])
+    prec = mx.MxGeoMultigridPrec(ctx, ops, R, P, smoother_sweeps=2)
+    b = mx.MxMultiVector(maps[0], 2, True)
+    b.random(8)
+    x = mx.MxMultiVector(maps[0], 2, True)
+    r = b.CloneCopy()
+    e = b.Clone(2)
+    norms = [b.norm2().max()]
+    for _ in range(5):
+        prec.ApplyInverse(r, e)
+        x.MvAddMv(1.0, x, 1.0, e)
+        r.assign(b)
+        ops[0].apply_axpby(-1.0, x, 1.0, r)
+        norms.append(r.norm2().max())
+    assert norms[-1] < 0.05 * norms[0], norms

@@ -178,8 +178,6 @@ def test_host_buffer_batch_apply(mx, ctx, orc, is_complex):
     A.apply_host_batch([], [])
 
 
-@pytest.mark.xfail(strict=False, reason="component-major ordered maps: host half validated on the CPU (tests/test_ilv_model.py); "
-                                        "the device half was written after the round's GPU budget ran out and has not run yet")
 def test_component_major_ordered_maps():
     """mxg_map_create_ordered: vectors stored component-major on the device, operators re-indexed at creation. Results must
     equal the reference order bit for bit. Runs in its own process (tests/ordered_map_check.py)."""
@@ -190,3 +188,42 @@ def test_component_major_ordered_maps():
     res = subprocess.run([sys.executable, os.path.join(root, "tests", "ordered_map_check.py")], capture_output=True, text=True,
                          timeout=600)
     assert res.returncode == 0 and "ORDERED MAPS OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_literal_reference_operator_r13(mx, ctx, orc):
+    """DESIGN.md R13: read literally, MxYeeFitEField::getCompFactor (MxYeeFitEField.cpp:90-98) drops curlE's wrap-around
+    entries on a periodic upper boundary (MxGridField.cpp:64-74). The oracle can generate that operator too
+    (literal_upper_periodic_e); the GPU apply must be bit-exact on it as on the default one -- parity is with whatever
+    operator the host hands over."""
+    lit, dflt = orc.vacuum(12, literal=True), orc.vacuum(12)
+    _, op_l, ref_l, got_l, _, _ = _apply_case(mx, ctx, orc, lit, "curlCurl", 3, None)
+    _, op_d, ref_d, got_d, _, _ = _apply_case(mx, ctx, orc, dflt, "curlCurl", 3, None)
+    assert op_l.nnz < op_d.nnz                      # the literal operator lost its wrap-around couplings
+    assert np.array_equal(ref_l, got_l) and np.array_equal(ref_d, got_d)
+    assert not np.array_equal(got_l, got_d)
+
+
+@pytest.mark.parametrize("name,size", [("curlCurl", 48), ("vecLapl", 40), ("scaLapl", 40)])
+def test_windowed_kernel_equals_gather_kernel(mx, ctx, orc, name, size, monkeypatch):
+    """The windowed dictionary kernel (x windows staged in shared memory by 1-D TMA, mxg_spmm_win.cuh) against the gather
+    kernels (MXG_SPMV_WIN=0) and the oracle, on grids large enough for many tiles; block applies and the fused epilogue."""
+    sim = orc.pillbox(size)
+    monkeypatch.setenv("MXG_SPMV_WIN", "1")
+    Aw, op, rmap, cmap = gpu_matrix(mx, ctx, sim, name)
+    monkeypatch.setenv("MXG_SPMV_WIN", "0")
+    Ag, _, _, _ = gpu_matrix(mx, ctx, sim, name)
+    for nvec in (1, 3, 8):
+        x = mx.MxMultiVector(cmap, nvec)
+        yw = mx.MxMultiVector(rmap, nvec)
+        yg = mx.MxMultiVector(rmap, nvec)
+        x.random(99 + nvec)
+        Aw.apply(x, yw)
+        Ag.apply(x, yg)
+        ref = op.apply(x.to_host())
+        assert np.array_equal(yg.to_host(), ref)
+        assert np.array_equal(yw.to_host(), ref), (name, nvec, rel_err(yw.to_host(), ref))
+        yw.random(5)
+        yg.assign(yw)
+        Aw.apply_axpby(-1.0, x, 1.0, yw)
+        Ag.apply_axpby(-1.0, x, 1.0, yg)
+        assert np.array_equal(yw.to_host(), yg.to_host())
