@@ -985,6 +985,9 @@ class MxDivProjector : public mx::Operator<Scalar>, public mx::Constraint<Scalar
     numLinIters += krylov_.pcg(A, T, psi1, psi2, tol, maxIters_);                            // (:903-913)
     const double one[2] = {1.0, 0.0};
     mx::check(mxg_crs_apply_axpby(G_, one, psi2.getRawMV(), one, b2.getRawMV()));            // y = gradPsi psi2 + bWork (:919-921)
+    // faces of zero area are invisible to M but gradPsi writes them: keep them at zero (zeroUnusedComponents, which the
+    // reference has commented out at :928 and applies to the initial block only, MxSolver.cpp:65)
+    if (m_) mx::check(mxg_mv_zero_unused(b2.getRawMV(), m_));
     ++numApplies;
     numColumns += nb;
   }

@@ -102,6 +102,7 @@ int mxg_ctx_create(int device, mxg_ctx** out) {
   MXG_CUDA(cudaHostAlloc(&ctx->hErr, sizeof(int), cudaHostAllocMapped));
   *ctx->hErr = 0;
   MXG_CUDA(cudaHostGetDevicePointer(&ctx->dErr, ctx->hErr, 0));
+  MXG_CUDA(cudaMalloc(&ctx->dDense, 64 * 1024));
   int rc = ensureScratch(ctx, 1u << 20);
   if (rc) return rc;
   rc = ensurePinned(ctx, 1u << 20);
@@ -117,6 +118,7 @@ int mxg_ctx_destroy(mxg_ctx* ctx) {
   cudaStreamSynchronize(ctx->commStream);
   if (ctx->comm) ncclCommDestroy(ctx->comm);
   if (ctx->dScratch) cudaFree(ctx->dScratch);
+  if (ctx->dDense) cudaFree(ctx->dDense);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
   if (ctx->hErr) cudaFreeHost(ctx->hErr);
   cudaEventDestroy(ctx->evA);

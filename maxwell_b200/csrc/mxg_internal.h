@@ -97,6 +97,7 @@ struct mxg_ctx {
   int rank = 0, nranks = 1;
   double* dScratch = nullptr;          // reduction partials / small device results
   size_t scratchBytes = 0;
+  double* dDense = nullptr;            // device copy of the small dense B of the update product (kDenseBBytes)
   double* hPinned = nullptr;           // pinned host staging for small results and dense B
   size_t pinnedBytes = 0;
   int64_t launches = 0;

@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "mxg_internal.h"
+#include "mxg_dense.cuh"
 
 using namespace mxg;
 
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_gram_tiled(ColTable<double> A, in
 // ---- tall-skinny update: Y = alpha * A * B + beta * Y ---------------------------------------
 // The small dense B rides in the kernel parameter block (constant bank): the FMAs take it as a
 // uniform operand, so the only memory instructions are the streaming loads of A and Y.
+constexpr int kUpdateMaxK = 64;   // widest A the TMA-staged update kernel takes (shared memory: 2 stages of k columns + B)
 constexpr int kMaxBParam = 1536;  // doubles (12 KB of the 32 KB parameter space)
 struct DenseParam {
   double v[kMaxBParam];
@@ -441,11 +443,11 @@ int transMvImpl(const double alpha[2], const mxg_mv* A, const mxg_mv* X, double*
   const size_t kb = size_t(k) * b;
   // shared-memory tiled kernel (real case): the block tile of C is (16 ri) x (16 rj) with ri, rj in 1..4
   // chosen to cover k and b with as little padding as possible
-  const int ri = k >= 49 ? 4 : (k + 15) / 16, rj = b >= 49 ? 4 : (b + 15) / 16;
+  const int ri = k >= 33 ? 3 : (k + 15) / 16, rj = b >= 33 ? 3 : (b + 15) / 16;   // block tile (16 ri) x (16 rj), at most 48 x 48
   const int gtB = (b + 16 * rj - 1) / (16 * rj), gtiles = ((k + 16 * ri - 1) / (16 * ri)) * gtB;
   int gs = (ctx->numSMs * 2 + gtiles - 1) / gtiles;
   {
-    const int64_t chunks = (A->ld + kGramRows - 1) / kGramRows;
+    const int64_t chunks = (A->ld + kDenseRows - 1) / kDenseRows;
     if (gs > chunks) gs = int(chunks);
     if (gs < 1) gs = 1;
   }
@@ -455,15 +457,20 @@ int transMvImpl(const double alpha[2], const mxg_mv* A, const mxg_mv* X, double*
   T* out = reinterpret_cast<T*>(ctx->dScratch);
   T* partial = out + kb;
   if constexpr (w == 1) {
-    const dim3 grid(gtiles, gs);
     auto ta = tableOf<double>(A), tx = tableOf<double>(X);
     double* part = reinterpret_cast<double*>(partial);
-#define MXG_GRAM(RI, RJ) k_gram_tiled<RI, RJ><<<grid, kBlock, 0, ctx->stream>>>(ta, k, tx, b, A->ld, gtB, part)
+    const dim3 grid(gtiles, gs);
+    const size_t smem = 128 + size_t(2) * (16 * ri + 16 * rj) * kDenseStride * sizeof(double);
+#define MXG_GRAM(RI, RJ)                                                                                              \
+  {                                                                                                                   \
+    static bool attr = false;                                                                                         \
+    if (!attr) { MXG_CUDA(cudaFuncSetAttribute(k_gram_tma<RI, RJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; } \
+    k_gram_tma<RI, RJ><<<grid, kDenseThreads, smem, ctx->stream>>>(ta, k, tx, b, A->ld, gtB, part);                    \
+  }
     switch (ri * 4 + rj) {
-      case 5: MXG_GRAM(1, 1); break;  case 6: MXG_GRAM(1, 2); break;  case 7: MXG_GRAM(1, 3); break;  case 8: MXG_GRAM(1, 4); break;
-      case 9: MXG_GRAM(2, 1); break;  case 10: MXG_GRAM(2, 2); break; case 11: MXG_GRAM(2, 3); break; case 12: MXG_GRAM(2, 4); break;
-      case 13: MXG_GRAM(3, 1); break; case 14: MXG_GRAM(3, 2); break; case 15: MXG_GRAM(3, 3); break; case 16: MXG_GRAM(3, 4); break;
-      case 17: MXG_GRAM(4, 1); break; case 18: MXG_GRAM(4, 2); break; case 19: MXG_GRAM(4, 3); break; default: MXG_GRAM(4, 4); break;
+      case 5: MXG_GRAM(1, 1); break;  case 6: MXG_GRAM(1, 2); break;  case 7: MXG_GRAM(1, 3); break;
+      case 9: MXG_GRAM(2, 1); break;  case 10: MXG_GRAM(2, 2); break; case 11: MXG_GRAM(2, 3); break;
+      case 13: MXG_GRAM(3, 1); break; case 14: MXG_GRAM(3, 2); break; default: MXG_GRAM(3, 3); break;
     }
 #undef MXG_GRAM
   } else {
@@ -495,6 +502,33 @@ int timesMatImpl(const double alpha[2], const mxg_mv* A, const double* B, int ld
   const int k = A->ncols, b = Y->ncols;
   const T al = scalarOf<T>(alpha), be = scalarOf<T>(beta);
   const bool useY = !isZero(be);
+  if constexpr (w == 1) {
+    if (k <= kUpdateMaxK) {
+      // TMA-staged kernel: A is streamed once per block of <= 48 output columns
+      for (int c0 = 0; c0 < b; c0 += 48) {
+        const int cc = std::min(48, b - c0);
+        std::vector<double> Bc(size_t(k) * cc);
+        for (int j = 0; j < cc; ++j) std::memcpy(&Bc[size_t(j) * k], B + size_t(c0 + j) * ldb, sizeof(double) * k);
+        MXG_CUDA(cudaMemcpyAsync(ctx->dDense, Bc.data(), Bc.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        const int rc_ = (cc + 15) / 16;
+        const size_t smem = 128 + sizeof(double) * (((size_t(k) * 16 * rc_ + 15) & ~size_t(15)) + size_t(2) * k * kDenseStride);
+        const int64_t chunks = (Y->ld + kDenseRows - 1) / kDenseRows;
+        const int grid = int(std::min<int64_t>(chunks, int64_t(ctx->numSMs) * 2));
+        auto ta = tableOf<double>(A);
+        auto ty = tableOf<double>(Y, c0, cc);
+#define MXG_UPD(RC)                                                                                                    \
+  {                                                                                                                    \
+    static bool attr = false;                                                                                          \
+    if (!attr) { MXG_CUDA(cudaFuncSetAttribute(k_update_tma<RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; } \
+    k_update_tma<RC><<<grid, kDenseThreads, smem, ctx->stream>>>(ta, k, ctx->dDense, cc, al, be, ty, Y->ld);            \
+  }
+        if (rc_ == 1) MXG_UPD(1) else if (rc_ == 2) MXG_UPD(2) else MXG_UPD(3)
+#undef MXG_UPD
+        LAUNCH_CHECK(ctx);
+      }
+      return MXG_OK;
+    }
+  }
   // columns of B that fit in one parameter block
   const int colsPerLaunch = kMaxBParam / (k * w);
   MXG_REQUIRE(colsPerLaunch >= 1, "mxg_mv_times_mat_add_mv: A has too many columns (%d) for one pass", k);
@@ -766,7 +800,10 @@ int mxg_mv_times_mat_add_mv(const double alpha[2], const mxg_mv* A, const double
   int rc = checkSame("mxg_mv_times_mat_add_mv", A, Y, false);
   if (rc) return rc;
   MXG_REQUIRE(alpha && beta && B && ldb >= A->ncols, "mxg_mv_times_mat_add_mv: bad B / ldb (need ldb >= %d)", A->ncols);
-  MXG_REQUIRE(!overlaps(A, Y), "mxg_mv_times_mat_add_mv: A and Y must not share columns");
+  // Y may share columns with A (in-place right-multiplication of a basis block) on the TMA-staged real kernel, which holds
+  // a row chunk of A completely in shared memory before it writes those rows; otherwise the operands must be disjoint
+  const bool inPlaceOk = !A->isComplex && A->ncols <= kUpdateMaxK && Y->ncols <= 48;
+  MXG_REQUIRE(inPlaceOk || !overlaps(A, Y), "mxg_mv_times_mat_add_mv: A and Y must not share columns (complex, > %d source or > 48 result columns)", kUpdateMaxK);
   MXG_CUDA(cudaSetDevice(A->map->ctx->device));
   return A->isComplex ? timesMatImpl<zd>(alpha, A, B, ldb, beta, Y) : timesMatImpl<double>(alpha, A, B, ldb, beta, Y);
 }

@@ -239,7 +239,7 @@ __device__ __forceinline__ void winIssue(const WinTile& W, const T* __restrict__
   }
 }
 
-constexpr int kWinSlot = 16;   // pattern entries a per-warp slot holds (longer / non-uniform rows read the table directly)
+constexpr int kWinRegs = 14;   // pattern entries a thread keeps in registers (longer / non-uniform rows read the table per lane)
 
 template <class T>
 __device__ __forceinline__ PatEntry<T> ldEntry(const PatEntry<T>* p) {
@@ -248,15 +248,53 @@ __device__ __forceinline__ PatEntry<T> ldEntry(const PatEntry<T>* p) {
   const int4* s = reinterpret_cast<const int4*>(p);
   int4* d = reinterpret_cast<int4*>(&e);
 #pragma unroll
-  for (int i = 0; i < int(sizeof(PatEntry<T>) / 16); ++i) d[i] = s[i];
+  for (int i = 0; i < int(sizeof(PatEntry<T>) / 16); ++i) d[i] = __ldg(s + i);
   return e;
 }
 
 struct WinShift {
   int32_t dLo, dHi, s0, s1, s2;
+  __device__ __forceinline__ int32_t of(int32_t d) const { return d + (d < dLo ? s0 : (d > dHi ? s2 : s1)); }
 };
-// one row: entries from `ent` (per-warp shared slot or the global pattern table), x from the shared windows; ascending
-// column order with separately rounded multiply and add, as everywhere in this file
+
+// Pattern of a warp-uniform row group held in registers: value + shared-memory offset per entry. Loaded once per tile
+// and reused for every row of the thread and every vector of the block, so the inner loop is one shared gather per
+// (row, entry): ncu on the previous version (entries re-read from shared memory per row) showed 54 shared wavefronts and
+// 270 issued instructions per 32 rows, both near their limits (profiles/README_r02.md).
+template <class T>
+struct RegPattern {
+  T v[kWinRegs];
+  int32_t off[kWinRegs];
+  int32_t len;
+  __device__ __forceinline__ void load(const PatEntry<T>* __restrict__ pat, int32_t n, const WinShift& w) {
+    len = n;
+#pragma unroll
+    for (int q = 0; q < kWinRegs; ++q) {
+      v[q] = zeroOf<T>();
+      off[q] = 0;
+      if (q < n) {
+        const PatEntry<T> e = ldEntry<T>(pat + q);
+        v[q] = entryVal(e);
+        off[q] = w.of(e.d);
+      }
+    }
+  }
+  // NR rows of this thread: r[i] = r0 + i * stride; ascending column order, separately rounded multiply and add
+  template <int NR>
+  __device__ __forceinline__ void dot(const T* __restrict__ xs, int32_t r0, int32_t stride, T (&acc)[NR]) const {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) acc[i] = zeroOf<T>();
+#pragma unroll
+    for (int q = 0; q < kWinRegs; ++q)
+      if (q < len) {
+        const T* px = xs + r0 + off[q];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) accum(acc[i], v[q], px[i * stride]);
+      }
+  }
+};
+
+// per-lane fallback: entries from the global pattern table, x from the shared windows
 template <class T>
 __device__ __forceinline__ T winRowDot(const PatEntry<T>* __restrict__ ent, int32_t len, int32_t r, const T* __restrict__ xs, const WinShift& w) {
   T acc = zeroOf<T>();
@@ -264,18 +302,21 @@ __device__ __forceinline__ T winRowDot(const PatEntry<T>* __restrict__ ent, int3
   for (; q + 1 < len; q += 2) {
     const PatEntry<T> e0 = ldEntry<T>(ent + q);
     const PatEntry<T> e1 = ldEntry<T>(ent + q + 1);
-    const T x0 = xs[r + e0.d + (e0.d < w.dLo ? w.s0 : (e0.d > w.dHi ? w.s2 : w.s1))];
-    const T x1 = xs[r + e1.d + (e1.d < w.dLo ? w.s0 : (e1.d > w.dHi ? w.s2 : w.s1))];
+    const T x0 = xs[r + w.of(e0.d)];
+    const T x1 = xs[r + w.of(e1.d)];
     accum(acc, entryVal(e0), x0);
     accum(acc, entryVal(e1), x1);
   }
   if (q < len) {
     const PatEntry<T> e0 = ldEntry<T>(ent + q);
-    accum(acc, entryVal(e0), xs[r + e0.d + (e0.d < w.dLo ? w.s0 : (e0.d > w.dHi ? w.s2 : w.s1))]);
+    accum(acc, entryVal(e0), xs[r + w.of(e0.d)]);
   }
   return acc;
 }
 
+// ILV = 3: a warp owns 32 * RPT consecutive CELLS of one field component (lane l: cells l, l + 32, ...; rows are 3 apart
+// per cell, so one thread's rows are 96 apart and a warp reads the windows with stride 3 doubles: no bank conflict).
+// Three warps (components 0..2) cover a contiguous group of 96 * RPT rows. ILV = 1: lane l owns rows l, l + 32, ...
 template <class T, int ILV, int RPT>
 __global__ void __launch_bounds__(kWinThreads) k_spmm_win(int64_t rowBegin, int64_t rowEnd, int64_t tile0, DictArgs<T> D,
                                                           const WinTile* __restrict__ tiles, XSource<T> X, ColTable<T> Y, int nvec,
@@ -283,9 +324,7 @@ __global__ void __launch_bounds__(kWinThreads) k_spmm_win(int64_t rowBegin, int6
   extern __shared__ __align__(128) unsigned char smemRaw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smemRaw);
   WinTile* Ws = reinterpret_cast<WinTile*>(smemRaw + 64);
-  PatEntry<T>* slots = reinterpret_cast<PatEntry<T>*>(smemRaw + 128);
-  constexpr int kWarps = kWinThreads / 32;
-  T* buf = reinterpret_cast<T*>(smemRaw + 128 + sizeof(PatEntry<T>) * kWarps * RPT * kWinSlot);
+  T* buf = reinterpret_cast<T*>(smemRaw + 128);
   constexpr int R = kWinThreads * RPT;
   const int64_t tile = tile0 + blockIdx.x;
   if (threadIdx.x == 0) {
@@ -298,44 +337,76 @@ __global__ void __launch_bounds__(kWinThreads) k_spmm_win(int64_t rowBegin, int6
     if (Ws->valid) winIssue<T>(*Ws, X.x.p[0], buf, bar);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tOff = ILV == 3 ? (warp / 3) * 96 + 3 * lane + (warp % 3) : int(threadIdx.x);
-  int64_t row[RPT];
-  int32_t o[RPT], len[RPT];
-  bool uni[RPT];
+  constexpr int rowStride = 32 * ILV;   // distance between a thread's consecutive rows
+  const int64_t row0 = tile * R + (ILV == 3 ? (warp / 3) * (96 * RPT) + 3 * lane + (warp % 3) : warp * (32 * RPT) + lane);
+  int32_t p[RPT], o[RPT], len[RPT];
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
-    row[i] = tile * R + i * kWinThreads + tOff;
-    int32_t p = -1;
-    if (row[i] >= rowBegin && row[i] < rowEnd) p = D.rowPat[row[i]];
+    const int64_t row = row0 + i * rowStride;
+    p[i] = -1;
+    if (row >= rowBegin && row < rowEnd) p[i] = D.rowPat[row];
     o[i] = len[i] = 0;
-    if (p >= 0) { o[i] = __ldg(D.patOff + p); len[i] = __ldg(D.patOff + p + 1) - o[i]; }
-    // warp-uniform pattern (lanes without a dictionary row do not count): stage its entries once for the whole warp
-    const int32_t pmax = __reduce_max_sync(0xffffffffu, p);
-    uni[i] = __all_sync(0xffffffffu, p < 0 || p == pmax) && pmax >= 0;
-    const int32_t oU = __shfl_sync(0xffffffffu, o[i], __ffs(__ballot_sync(0xffffffffu, p == pmax)) - 1);
-    const int32_t lenU = __shfl_sync(0xffffffffu, len[i], __ffs(__ballot_sync(0xffffffffu, p == pmax)) - 1);
-    uni[i] = uni[i] && lenU <= kWinSlot;
-    if (uni[i] && lane < lenU) slots[(warp * RPT + i) * kWinSlot + lane] = ldEntry<T>(D.pat + oU + lane);
+    if (p[i] >= 0) { o[i] = __ldg(D.patOff + p[i]); len[i] = __ldg(D.patOff + p[i] + 1) - o[i]; }
+  }
+  // warp-uniform pattern over ALL rows of the warp (lanes without a dictionary row do not count)
+  int32_t pm = p[0];
+#pragma unroll
+  for (int i = 1; i < RPT; ++i) pm = max(pm, p[i]);
+  const int32_t pmax = __reduce_max_sync(0xffffffffu, pm);
+  bool mine = true;
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) mine = mine && (p[i] < 0 || p[i] == pmax);
+  bool uniAll = __all_sync(0xffffffffu, mine) && pmax >= 0;
+  int32_t oU = 0, lenU = 0;
+  if (uniAll) {
+    int32_t oc = 0, lc = 0;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+      if (p[i] == pmax) { oc = o[i]; lc = len[i]; }
+    const int src = __ffs(__ballot_sync(0xffffffffu, pm == pmax)) - 1;
+    oU = __shfl_sync(0xffffffffu, oc, src);
+    lenU = __shfl_sync(0xffffffffu, lc, src);
+    uniAll = lenU <= kWinRegs;
   }
   __syncthreads();
   if (!Ws->valid) {   // tile-uniform: gather path
 #pragma unroll
-    for (int i = 0; i < RPT; ++i)
-      if (row[i] >= rowBegin && row[i] < rowEnd) dictRow<T, false, 1>(row[i], D, X, Y, nvec, ep);
+    for (int i = 0; i < RPT; ++i) {
+      const int64_t row = row0 + i * rowStride;
+      if (row >= rowBegin && row < rowEnd) dictRow<T, false, 1>(row, D, X, Y, nvec, ep);
+    }
     return;
   }
-  const int32_t dLo = Ws->dLo, dHi = Ws->dHi, s0 = Ws->shift[0], s1 = Ws->shift[1], s2 = Ws->shift[2];
+  const WinShift ws{Ws->dLo, Ws->dHi, Ws->shift[0], Ws->shift[1], Ws->shift[2]};
+  RegPattern<T> P;
+  if (uniAll) P.load(D.pat + oU, lenU, ws);
+  const T* __restrict__ xs = buf;
   for (int j = 0; j < nvec; ++j) {
     mbarWait(bar, j & 1);
-    const T* __restrict__ xs = buf;
+    T* __restrict__ y = Y.p[j];
+    if (uniAll) {
+      T acc[RPT];
+      P.template dot<RPT>(xs, int32_t(row0), rowStride, acc);
 #pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-      if (len[i] == 0) continue;
-      const int32_t r = int32_t(row[i]);
-      const WinShift ws{dLo, dHi, s0, s1, s2};
-      const T acc = uni[i] ? winRowDot<T>(slots + (warp * RPT + i) * kWinSlot, len[i], r, xs, ws)
-                           : winRowDot<T>(D.pat + o[i], len[i], r, xs, ws);
-      storeY(Y.p[j], row[i], acc, ep);
+      for (int i = 0; i < RPT; ++i)
+        if (p[i] >= 0) storeY(y, row0 + i * rowStride, acc[i], ep);
+    } else {
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        // half-warp-uniform rows (a z-line ends inside this warp's cells) still share one pattern per row slot
+        const int32_t pmx = __reduce_max_sync(0xffffffffu, p[i]);
+        const bool uni = __all_sync(0xffffffffu, p[i] < 0 || p[i] == pmx) && pmx >= 0 &&
+                         __shfl_sync(0xffffffffu, len[i], __ffs(__ballot_sync(0xffffffffu, p[i] == pmx)) - 1) <= kWinRegs;
+        if (uni) {
+          const int src = __ffs(__ballot_sync(0xffffffffu, p[i] == pmx)) - 1;
+          P.load(D.pat + __shfl_sync(0xffffffffu, o[i], src), __shfl_sync(0xffffffffu, len[i], src), ws);   // P is free here
+          T acc[1];
+          P.template dot<1>(xs, int32_t(row0 + i * rowStride), 0, acc);
+          if (p[i] >= 0) storeY(y, row0 + i * rowStride, acc[0], ep);
+        } else if (len[i] > 0) {
+          storeY(y, row0 + i * rowStride, winRowDot<T>(D.pat + o[i], len[i], int32_t(row0 + i * rowStride), xs, ws), ep);
+        }
+      }
     }
     if (j + 1 < nvec) {
       __syncthreads();   // everyone is done with the windows of vector j
@@ -442,30 +513,29 @@ template <> struct WinCfg<zd> { static constexpr int RPT = 1; };
 constexpr size_t kWinSmemMax = 200 * 1024;      // per CTA
 constexpr size_t kWinBufBudget = 100 * 1024;    // one window set
 template <class T>
-constexpr size_t winSmemHeader() { return 128 + sizeof(PatEntry<T>) * (kWinThreads / 32) * WinCfg<T>::RPT * kWinSlot; }
+constexpr size_t winSmemHeader() { return 128; }
+
+template <class T, int ILV, int RPT>
+int launchWinK(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, const XSource<T>& X, const ColTable<T>& Y, int nvec,
+               const Epilogue<T>& ep, cudaStream_t st) {
+  const int R = A->winR;
+  const int64_t tile0 = rowBegin / R, tiles = (rowEnd + R - 1) / R - tile0;
+  const size_t smem = winSmemHeader<T>() + size_t(A->winBufElems) * sizeof(T);
+  auto kern = k_spmm_win<T, ILV, RPT>;
+  static bool attrSet = false;
+  if (!attrSet) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWinSmemMax))); attrSet = true; }
+  kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, dictArgs<T>(A), static_cast<const WinTile*>(A->dWinTiles), X, Y, nvec, ep);
+  LAUNCH_CHECK(A->ctx);
+  return MXG_OK;
+}
 
 template <class T>
 int launchWin(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, const XSource<T>& X, const ColTable<T>& Y, int nvec,
               const Epilogue<T>& ep, cudaStream_t st) {
-  mxg_ctx* ctx = A->ctx;
   constexpr int RPT = WinCfg<T>::RPT;
-  const int R = A->winR;
-  const int64_t tile0 = rowBegin / R, tiles = (rowEnd + R - 1) / R - tile0;
-  const size_t smem = winSmemHeader<T>() + size_t(A->winBufElems) * sizeof(T);
-  const DictArgs<T> D = dictArgs<T>(A);
-  const WinTile* wt = static_cast<const WinTile*>(A->dWinTiles);
-  static bool attrSet[2] = {false, false};
-  if (A->winIlv == 3) {
-    auto kern = k_spmm_win<T, 3, RPT>;
-    if (!attrSet[0]) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWinSmemMax))); attrSet[0] = true; }
-    kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, D, wt, X, Y, nvec, ep);
-  } else {
-    auto kern = k_spmm_win<T, 1, RPT>;
-    if (!attrSet[1]) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWinSmemMax))); attrSet[1] = true; }
-    kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, D, wt, X, Y, nvec, ep);
-  }
-  LAUNCH_CHECK(ctx);
-  return MXG_OK;
+  const bool big = A->winR == kWinThreads * 2 * RPT;   // MXG_WIN_RPT: twice the rows per tile
+  if (A->winIlv == 3) return big ? launchWinK<T, 3, 2 * RPT>(A, rowBegin, rowEnd, X, Y, nvec, ep, st) : launchWinK<T, 3, RPT>(A, rowBegin, rowEnd, X, Y, nvec, ep, st);
+  return big ? launchWinK<T, 1, 2 * RPT>(A, rowBegin, rowEnd, X, Y, nvec, ep, st) : launchWinK<T, 1, RPT>(A, rowBegin, rowEnd, X, Y, nvec, ep, st);
 }
 
 template <class T, bool GHOST>
@@ -1123,7 +1193,8 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
     const char* env = std::getenv("MXG_SPMV_WIN");
     const bool want = !(env && std::strcmp(env, "0") == 0);
     if (want && A->dictRows > 0 && nLoc + A->gLo + A->gHi < (int64_t(1) << 30)) {
-      constexpr int R = kWinThreads * WinCfg<T>::RPT;
+      int R = kWinThreads * WinCfg<T>::RPT;
+      if (const char* e2 = std::getenv("MXG_WIN_RPT")) { if (std::atoi(e2) == 2 * WinCfg<T>::RPT) R *= 2; }
       constexpr int align = 16 / int(sizeof(T)) > 0 ? 16 / int(sizeof(T)) : 1;
       const PatEntry<T>* pe = pat.data();
       int64_t maxTotal = 0, valid = 0;

@@ -100,20 +100,24 @@ def test_projection_is_the_m_orthogonal_projector(mx, ctx, orc):
     x1 = X.to_host()
     Dm, Gm, Sm = opD.scipy(), opG.scipy(), opS.scipy()
     M = sp.diags(fa)
-    # (i) divergence free, (ii) the correction is a gradient field: CPU projection through a direct solve (constant pinned)
+    # (i) divergence free, (ii) the correction is a gradient field: CPU projection through a direct solve. Psi cells whose
+    # faces all have zero area give empty rows of scaLapl (left at zero by CG); the constant is pinned at one live cell.
     assert np.abs(Dm @ (M @ x1)).max() < 1e-9 * np.abs(Dm @ (M @ x0)).max()
     rhs = Dm @ (M @ x0)
+    live = np.where(np.abs(Sm.diagonal()) > 0)[0]
     psi = np.zeros_like(rhs)
-    lu = sla.splu(Sm[1:, 1:].tocsc())
-    psi[1:] = lu.solve(rhs[1:])
+    lu = sla.splu(Sm[live[1:]][:, live[1:]].tocsc())
+    psi[live[1:]] = lu.solve(rhs[live[1:]])
     want = x0 + Gm @ psi
-    assert np.linalg.norm(x1 - want) < 1e-9 * np.linalg.norm(want)
+    used = fa > 0
+    assert np.all(x1[~used] == 0)
+    assert np.linalg.norm(x1[used] - want[used]) < 1e-8 * np.linalg.norm(want[used])
     # (iii) M-orthogonality of the split
     for j in range(3):
         assert abs(x1[:, j] @ (fa * (x0[:, j] - x1[:, j]))) < 1e-9 * (x0[:, j] @ (fa * x0[:, j]))
     # idempotent
     mx.div_project(ctx, md, X, D, G, S, tol=1e-12)
-    assert np.linalg.norm(X.to_host() - x1) < 1e-9 * np.linalg.norm(x1)
+    assert np.linalg.norm(X.to_host() - x1) < 1e-8 * np.linalg.norm(x1)
 
 
 @pytest.mark.parametrize("lin_solver,sigma", [("cg", 0.05 * (2 * np.pi) ** 2), ("bicgstab", 45.0), ("gmres", 45.0)])
@@ -145,8 +149,9 @@ def test_magwave_apply_matches_cpu_shift_invert(mx, ctx, orc, lin_solver, sigma)
     b[keep] = sla.splu((L - sigma * M).tocsc()).solve(fa[keep, None] * x[keep])
     Dm, Gm, Sm = opD.scipy(), opG.scipy(), opS.scipy()
     rhs = Dm @ (fa[:, None] * b)
+    live = np.where(np.abs(Sm.diagonal()) > 0)[0]
     psi = np.zeros_like(rhs)
-    psi[1:] = sla.splu(Sm[1:, 1:].tocsc()).solve(rhs[1:])
+    psi[live[1:]] = sla.splu(Sm[live[1:]][:, live[1:]].tocsc()).solve(rhs[live[1:]])
     want = b + Gm @ psi
     err = np.linalg.norm(y[keep] - want[keep]) / np.linalg.norm(want[keep])
     assert err < 1e-7, (lin_solver, err, op.num_vec_lin_iters)

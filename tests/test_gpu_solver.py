@@ -20,7 +20,7 @@ def _hierarchy(mx, ctx, orc, make_sim, sizes, name="vecLapl"):
         maps.append(rmap)
     R, P = [], []
     for l in range(len(sims) - 1):
-        p = orc.interpolator(sims[l + 1], sims[l])        # coarse -> fine (refiner, MxGridFieldInterpolator)
+        p = orc.interpolator(sims[l + 1], sims[l], is_complex=sims[0].is_complex)   # coarse -> fine (refiner, MxGridFieldInterpolator)
         # fine -> coarse: P^T / 2^d. The reference spec interpolates in both directions
         # (MxGeoMultigridPrec.cpp:438-452), which diverges on cut-cell operators (GMG notes).
         r = p.transpose(scale=1.0 / 8.0)
