@@ -348,26 +348,14 @@ __global__ void __launch_bounds__(kWinThreads) k_spmm_win(int64_t rowBegin, int6
     o[i] = len[i] = 0;
     if (p[i] >= 0) { o[i] = __ldg(D.patOff + p[i]); len[i] = __ldg(D.patOff + p[i] + 1) - o[i]; }
   }
-  // warp-uniform pattern over ALL rows of the warp (lanes without a dictionary row do not count)
-  int32_t pm = p[0];
+  // one pattern for ALL rows of the warp? (every lane, every row slot: a lane without a dictionary row would read
+  // outside the staged windows, so such warps take the per-slot paths below)
+  const int32_t pmax = __shfl_sync(0xffffffffu, p[0], 0);
+  bool mine = pmax >= 0;
 #pragma unroll
-  for (int i = 1; i < RPT; ++i) pm = max(pm, p[i]);
-  const int32_t pmax = __reduce_max_sync(0xffffffffu, pm);
-  bool mine = true;
-#pragma unroll
-  for (int i = 0; i < RPT; ++i) mine = mine && (p[i] < 0 || p[i] == pmax);
-  bool uniAll = __all_sync(0xffffffffu, mine) && pmax >= 0;
-  int32_t oU = 0, lenU = 0;
-  if (uniAll) {
-    int32_t oc = 0, lc = 0;
-#pragma unroll
-    for (int i = 0; i < RPT; ++i)
-      if (p[i] == pmax) { oc = o[i]; lc = len[i]; }
-    const int src = __ffs(__ballot_sync(0xffffffffu, pm == pmax)) - 1;
-    oU = __shfl_sync(0xffffffffu, oc, src);
-    lenU = __shfl_sync(0xffffffffu, lc, src);
-    uniAll = lenU <= kWinRegs;
-  }
+  for (int i = 0; i < RPT; ++i) mine = mine && p[i] == pmax;
+  const bool uniAll = __all_sync(0xffffffffu, mine) && len[0] <= kWinRegs;
+  const int32_t oU = o[0], lenU = len[0];
   __syncthreads();
   if (!Ws->valid) {   // tile-uniform: gather path
 #pragma unroll
@@ -388,21 +376,18 @@ __global__ void __launch_bounds__(kWinThreads) k_spmm_win(int64_t rowBegin, int6
       T acc[RPT];
       P.template dot<RPT>(xs, int32_t(row0), rowStride, acc);
 #pragma unroll
-      for (int i = 0; i < RPT; ++i)
-        if (p[i] >= 0) storeY(y, row0 + i * rowStride, acc[i], ep);
+      for (int i = 0; i < RPT; ++i) storeY(y, row0 + i * rowStride, acc[i], ep);
     } else {
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
-        // half-warp-uniform rows (a z-line ends inside this warp's cells) still share one pattern per row slot
-        const int32_t pmx = __reduce_max_sync(0xffffffffu, p[i]);
-        const bool uni = __all_sync(0xffffffffu, p[i] < 0 || p[i] == pmx) && pmx >= 0 &&
-                         __shfl_sync(0xffffffffu, len[i], __ffs(__ballot_sync(0xffffffffu, p[i] == pmx)) - 1) <= kWinRegs;
+        // a z-line ends inside this warp's cells: row slots that are still uniform share one pattern
+        const int32_t pmx = __shfl_sync(0xffffffffu, p[i], 0);
+        const bool uni = __all_sync(0xffffffffu, p[i] == pmx && pmx >= 0) && len[i] <= kWinRegs;
         if (uni) {
-          const int src = __ffs(__ballot_sync(0xffffffffu, p[i] == pmx)) - 1;
-          P.load(D.pat + __shfl_sync(0xffffffffu, o[i], src), __shfl_sync(0xffffffffu, len[i], src), ws);   // P is free here
+          P.load(D.pat + o[i], len[i], ws);   // P is free here
           T acc[1];
           P.template dot<1>(xs, int32_t(row0 + i * rowStride), 0, acc);
-          if (p[i] >= 0) storeY(y, row0 + i * rowStride, acc[0], ep);
+          storeY(y, row0 + i * rowStride, acc[0], ep);
         } else if (len[i] > 0) {
           storeY(y, row0 + i * rowStride, winRowDot<T>(D.pat + o[i], len[i], int32_t(row0 + i * rowStride), xs, ws), ep);
         }
