@@ -102,7 +102,15 @@ class MxMultiVector {
     if (vals.size() != getNumVecs()) throw std::runtime_error("MxMultiVector::scale: one scalar per column expected");
     mx::check(mxg_mv_scale_cols(mv_, reinterpret_cast<const double*>(vals.data())));
   }
-  virtual void random() { mx::check(mxg_mv_random(mv_, seed_)); }
+  // uniform (-1,1) keyed by (seed, call epoch of the context, global DOF id, column): every call draws new numbers
+  // (Epetra's Random() advances its state), identical on every rank count
+  virtual void random() {
+    const uint64_t ep = mxg_ctx_random_epoch(map_->getComm()->raw());
+    uint64_t z = seed_ + 0x9E3779B97F4A7C15ull * (ep + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    mx::check(mxg_mv_random(mv_, ep == 0 ? seed_ : (z ^ (z >> 31))));
+  }
   void setSeed(uint64_t seed) { seed_ = seed; }
   void norm2(std::vector<double>& norms) const { norms.resize(getNumVecs()); mx::check(mxg_mv_norm2(mv_, norms.data())); }
   // divides by the norm (the reference multiplies -- MxMultiVector.cpp:157-172)
@@ -186,6 +194,9 @@ class MxAnasaziMV : public mx::MultiVec<Scalar>, public MxMultiVector<Scalar> {
   static std::vector<size_t> toSize(const std::vector<int>& index) { return std::vector<size_t>(index.begin(), index.end()); }
 
  public:
+  // MvTimesMatAddMv accepts a result that shares columns with A (real scalars, <= 64 source / <= 48 result columns):
+  // the eigensolver right-multiplies basis blocks in place instead of through a temporary block + copy
+  static constexpr bool kTimesMatInPlace = !ST::isComplex;
   MxAnasaziMV(std::shared_ptr<MxMap> map, size_t numVecs) : MxMultiVector<Scalar>(map, numVecs) {}
   MxAnasaziMV(const MxMultiVector<Scalar>& mv) : MxMultiVector<Scalar>(mv) {}
   MxAnasaziMV(const MxMultiVector<Scalar>& mv, const std::vector<size_t>& vecInds, bool deepcopy)

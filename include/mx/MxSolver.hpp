@@ -415,10 +415,14 @@ class MxSolverT {
       // base(:, dstCols) = base(:, srcCols) * C  through the temp block (src and dst may overlap)
       timeit(res.tUpdate, [&] {
         auto src = view(base, srcCols);
-        auto t = view(tmp, range(0, C.numCols()));
-        t->MvTimesMatAddMv(S(1.0), *src, C, S(0.0));
         auto dst = view(base, dstCols);
-        *dst = *t;
+        if (MV::kTimesMatInPlace && srcCols.size() <= 64 && dstCols.size() <= 48) {
+          dst->MvTimesMatAddMv(S(1.0), *src, C, S(0.0));   // in place: one pass over the block
+        } else {
+          auto t = view(tmp, range(0, C.numCols()));
+          t->MvTimesMatAddMv(S(1.0), *src, C, S(0.0));
+          *dst = *t;
+        }
       });
     };
     auto gram = [&](MV& left, const std::vector<int>& lc, MV& right, const std::vector<int>& rc) {

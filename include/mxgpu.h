@@ -59,6 +59,10 @@ int mxg_ctx_num_ranks(const mxg_ctx* ctx);   /* MxComm::numProc */
  * any means (the tests use torch.distributed); then every rank calls mxg_ctx_comm_init. */
 int mxg_comm_unique_id(void* out /* MXG_UNIQUE_ID_BYTES */);
 int mxg_ctx_comm_init(mxg_ctx* ctx, int rank, int nranks, const void* unique_id);
+/* Counter that advances on every call: MxMultiVector::random() mixes it into its seed so that successive MvRandom calls --
+ * also on Clone()d blocks -- draw independent numbers, as Epetra's Random() does by advancing its state
+ * (MxMultiVector.hpp:41). Ranks that make the same calls see the same values, which keeps vectors rank-count invariant. */
+uint64_t mxg_ctx_random_epoch(mxg_ctx* ctx);
 /* raw handles for host code that wants to enqueue its own work or events */
 void* mxg_ctx_stream(mxg_ctx* ctx);          /* cudaStream_t */
 /* device timing on the ctx stream (CUDA events; slot in 0..15). The reference times with

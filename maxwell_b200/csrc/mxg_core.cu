@@ -40,6 +40,10 @@ int allReduceScratch(mxg_ctx* ctx, size_t count) {
   MXG_NCCL(ncclAllReduce(ctx->dScratch, ctx->dScratch, count, ncclDouble, ncclSum, ctx->comm, ctx->stream));
   return MXG_OK;
 }
+int checkHaloFault(const mxg_ctx* ctx, const char* where) {
+  MXG_REQUIRE(!ctx->hErr || *ctx->hErr == 0, "%s: a halo exchange timed out waiting for a neighbour rank (dead or dead-locked rank)", where);
+  return MXG_OK;
+}
 int mapGlobalCount(mxg_map* map, int64_t* out) {
   if (map->nMapGlobal < 0) {
     mxg_ctx* ctx = map->ctx;
@@ -102,6 +106,13 @@ int mxg_ctx_create(int device, mxg_ctx** out) {
   MXG_CUDA(cudaHostAlloc(&ctx->hErr, sizeof(int), cudaHostAllocMapped));
   *ctx->hErr = 0;
   MXG_CUDA(cudaHostGetDevicePointer(&ctx->dErr, ctx->hErr, 0));
+  {
+    double seconds = 120.0;
+    if (const char* e = std::getenv("MXG_HALO_TIMEOUT_S")) seconds = std::atof(e);
+    int khz = 0;
+    MXG_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+    ctx->haloTimeoutTicks = seconds > 0 ? (long long)(seconds * 1e3 * double(khz)) : 0;
+  }
   MXG_CUDA(cudaMalloc(&ctx->dDense, 64 * 1024));
   int rc = ensureScratch(ctx, 1u << 20);
   if (rc) return rc;
@@ -135,10 +146,14 @@ int mxg_ctx_destroy(mxg_ctx* ctx) {
 
 int mxg_ctx_sync(mxg_ctx* ctx) {
   MXG_REQUIRE(ctx != nullptr, "mxg_ctx_sync: ctx is NULL");
-  MXG_CUDA(cudaStreamSynchronize(ctx->commStream));
-  MXG_CUDA(cudaStreamSynchronize(ctx->stream));
+  const cudaError_t e1 = cudaStreamSynchronize(ctx->commStream), e2 = cudaStreamSynchronize(ctx->stream);
+  int rc = checkHaloFault(ctx, "mxg_ctx_sync");
+  if (rc) return rc;
+  MXG_CUDA(e1);
+  MXG_CUDA(e2);
   return MXG_OK;
 }
+uint64_t mxg_ctx_random_epoch(mxg_ctx* ctx) { return ctx ? ctx->randomEpoch++ : 0; }
 int mxg_ctx_rank(const mxg_ctx* ctx) { return ctx ? ctx->rank : 0; }
 int mxg_ctx_num_ranks(const mxg_ctx* ctx) { return ctx ? ctx->nranks : 1; }
 void* mxg_ctx_stream(mxg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -392,7 +407,12 @@ int mxg_mv_download(const mxg_mv* mv, double* host, int64_t ld) {
     if (mv->ld)
       MXG_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(host) + size_t(j) * ld * esz, mv->col[j], mv->ld * esz,
                                cudaMemcpyDeviceToHost, ctx->stream));
-  MXG_CUDA(cudaStreamSynchronize(ctx->stream));
+  {
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    int rc = checkHaloFault(ctx, "mxg_mv_download");
+    if (rc) return rc;
+    MXG_CUDA(e);
+  }
   return MXG_OK;
 }
 

@@ -104,6 +104,8 @@ struct mxg_ctx {
   bool graphsOff = false;              // set when stream capture of the halo apply is unavailable
   int* hErr = nullptr;                 // mapped pinned error word written by device-side waits
   int* dErr = nullptr;
+  long long haloTimeoutTicks = 0;      // device clock ticks a halo wait may spin (MXG_HALO_TIMEOUT_S; 0 = for ever)
+  uint64_t randomEpoch = 0;            // advanced by mxg_ctx_random_epoch: successive MvRandom calls draw new numbers
 };
 
 struct mxg_map {
@@ -180,6 +182,7 @@ struct mxg_crs {
   void* dWinTiles = nullptr;           // WinTile[winTiles]
   int winR = 0;                        // rows per tile (0 = windowed path off)
   int winIlv = 1;                      // thread -> row assignment inside a tile (1 or 3)
+  int winMaxVec = 1;                   // widest block the windowed kernel takes (wider blocks: gather kernels)
   int64_t winTiles = 0, winValid = 0;  // tiles / tiles served from shared memory
   int64_t winBufElems = 0;             // largest window set of any tile (scalars)
   // captured CUDA graphs of the multi-rank apply (pack -> NCCL exchange || interior rows -> boundary rows),
@@ -223,6 +226,8 @@ int ensurePinned(mxg_ctx* ctx, size_t bytes);
 int allReduceScratch(mxg_ctx* ctx, size_t count);
 // number of DOFs of the map over all ranks (collective on first use when the context has several ranks)
 int mapGlobalCount(mxg_map* map, int64_t* out);
+// fails when a device-side halo wait has recorded a dead neighbour rank
+int checkHaloFault(const mxg_ctx* ctx, const char* where);
 inline int gridFor(const mxg_ctx* ctx, int64_t work, int block, int perSM) {
   int64_t need = (work + block - 1) / block;
   int64_t cap = int64_t(ctx->numSMs) * perSM;

@@ -1,6 +1,7 @@
 // libmxgpu: multivector block operations (K5-K14 of SURVEY.md section 2.3). All kernels are
 // HBM-bound streaming or reduction kernels; grids are sized in multiples of the SM count.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "mxg_internal.h"
@@ -283,6 +284,12 @@ __global__ void __launch_bounds__(kBlock, 2) k_gram_tiled(ColTable<double> A, in
 // ---- tall-skinny update: Y = alpha * A * B + beta * Y ---------------------------------------
 // The small dense B rides in the kernel parameter block (constant bank): the FMAs take it as a
 // uniform operand, so the only memory instructions are the streaming loads of A and Y.
+// FP64 tensor-core (DMMA) variants of the Gram / update kernels unless MXG_DENSE=fma (mxg_dense.cuh)
+inline bool denseUseMma() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("MXG_DENSE"); v = (e && std::strcmp(e, "fma") == 0) ? 0 : 1; }
+  return v == 1;
+}
 constexpr int kUpdateMaxK = 64;   // widest A the TMA-staged update kernel takes (shared memory: 2 stages of k columns + B)
 constexpr int kMaxBParam = 1536;  // doubles (12 KB of the 32 KB parameter space)
 struct DenseParam {
@@ -423,7 +430,12 @@ int fetchScratch(mxg_ctx* ctx, double* host, size_t count) {
   int rc = ensurePinned(ctx, count * sizeof(double));
   if (rc) return rc;
   MXG_CUDA(cudaMemcpyAsync(ctx->hPinned, ctx->dScratch, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  MXG_CUDA(cudaStreamSynchronize(ctx->stream));
+  {
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    rc = checkHaloFault(ctx, "reduction");
+    if (rc) return rc;
+    MXG_CUDA(e);
+  }
   std::memcpy(host, ctx->hPinned, count * sizeof(double));
   return MXG_OK;
 }
@@ -451,7 +463,8 @@ int transMvImpl(const double alpha[2], const mxg_mv* A, const mxg_mv* X, double*
     if (gs > chunks) gs = int(chunks);
     if (gs < 1) gs = 1;
   }
-  if (w == 1) slices = gs;
+  const bool useMma = denseUseMma();
+  if (w == 1) slices = useMma ? 2 * gs : gs;   // the DMMA kernel writes its two row halves as separate slices
   int rc = ensureScratch(ctx, sizeof(T) * (kb * slices + kb));
   if (rc) return rc;
   T* out = reinterpret_cast<T*>(ctx->dScratch);
@@ -464,8 +477,13 @@ int transMvImpl(const double alpha[2], const mxg_mv* A, const mxg_mv* X, double*
 #define MXG_GRAM(RI, RJ)                                                                                              \
   {                                                                                                                   \
     static bool attr = false;                                                                                         \
-    if (!attr) { MXG_CUDA(cudaFuncSetAttribute(k_gram_tma<RI, RJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; } \
-    k_gram_tma<RI, RJ><<<grid, kDenseThreads, smem, ctx->stream>>>(ta, k, tx, b, A->ld, gtB, part);                    \
+    if (!attr) {                                                                                                      \
+      MXG_CUDA(cudaFuncSetAttribute(k_gram_tma<RI, RJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));     \
+      MXG_CUDA(cudaFuncSetAttribute(k_gram_mma<RI, RJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));     \
+      attr = true;                                                                                                    \
+    }                                                                                                                 \
+    if (useMma) k_gram_mma<RI, RJ><<<grid, kDenseThreads, smem, ctx->stream>>>(ta, k, tx, b, A->ld, gtB, part);        \
+    else k_gram_tma<RI, RJ><<<grid, kDenseThreads, smem, ctx->stream>>>(ta, k, tx, b, A->ld, gtB, part);               \
   }
     switch (ri * 4 + rj) {
       case 5: MXG_GRAM(1, 1); break;  case 6: MXG_GRAM(1, 2); break;  case 7: MXG_GRAM(1, 3); break;
@@ -512,6 +530,9 @@ int timesMatImpl(const double alpha[2], const mxg_mv* A, const double* B, int ld
         MXG_CUDA(cudaMemcpyAsync(ctx->dDense, Bc.data(), Bc.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         const int rc_ = (cc + 15) / 16;
         const size_t smem = 128 + sizeof(double) * (((size_t(k) * 16 * rc_ + 15) & ~size_t(15)) + size_t(2) * k * kDenseStride);
+        const size_t k4 = size_t((k + 3) & ~3);
+        const size_t smemMma = 128 + sizeof(double) * (((k4 * (16 * rc_ + 4) + 15) & ~size_t(15)) + size_t(2) * k4 * kDenseStride);
+        const bool useMma = denseUseMma();
         const int64_t chunks = (Y->ld + kDenseRows - 1) / kDenseRows;
         const int grid = int(std::min<int64_t>(chunks, int64_t(ctx->numSMs) * 2));
         auto ta = tableOf<double>(A);
@@ -519,8 +540,13 @@ int timesMatImpl(const double alpha[2], const mxg_mv* A, const double* B, int ld
 #define MXG_UPD(RC)                                                                                                    \
   {                                                                                                                    \
     static bool attr = false;                                                                                          \
-    if (!attr) { MXG_CUDA(cudaFuncSetAttribute(k_update_tma<RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; } \
-    k_update_tma<RC><<<grid, kDenseThreads, smem, ctx->stream>>>(ta, k, ctx->dDense, cc, al, be, ty, Y->ld);            \
+    if (!attr) {                                                                                                       \
+      MXG_CUDA(cudaFuncSetAttribute(k_update_tma<RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));        \
+      MXG_CUDA(cudaFuncSetAttribute(k_update_mma<RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));        \
+      attr = true;                                                                                                     \
+    }                                                                                                                  \
+    if (useMma) k_update_mma<RC><<<grid, kDenseThreads, smemMma, ctx->stream>>>(ta, k, ctx->dDense, cc, al, be, ty, Y->ld); \
+    else k_update_tma<RC><<<grid, kDenseThreads, smem, ctx->stream>>>(ta, k, ctx->dDense, cc, al, be, ty, Y->ld);       \
   }
         if (rc_ == 1) MXG_UPD(1) else if (rc_ == 2) MXG_UPD(2) else MXG_UPD(3)
 #undef MXG_UPD

@@ -239,7 +239,7 @@ __device__ __forceinline__ void winIssue(const WinTile& W, const T* __restrict__
   }
 }
 
-constexpr int kWinRegs = 14;   // pattern entries a thread keeps in registers (longer / non-uniform rows read the table per lane)
+constexpr int kWinSlot = 16;   // pattern entries a per-warp slot holds (longer / non-uniform rows read the table directly)
 
 template <class T>
 __device__ __forceinline__ PatEntry<T> ldEntry(const PatEntry<T>* p) {
@@ -248,53 +248,15 @@ __device__ __forceinline__ PatEntry<T> ldEntry(const PatEntry<T>* p) {
   const int4* s = reinterpret_cast<const int4*>(p);
   int4* d = reinterpret_cast<int4*>(&e);
 #pragma unroll
-  for (int i = 0; i < int(sizeof(PatEntry<T>) / 16); ++i) d[i] = __ldg(s + i);
+  for (int i = 0; i < int(sizeof(PatEntry<T>) / 16); ++i) d[i] = s[i];
   return e;
 }
 
 struct WinShift {
   int32_t dLo, dHi, s0, s1, s2;
-  __device__ __forceinline__ int32_t of(int32_t d) const { return d + (d < dLo ? s0 : (d > dHi ? s2 : s1)); }
 };
-
-// Pattern of a warp-uniform row group held in registers: value + shared-memory offset per entry. Loaded once per tile
-// and reused for every row of the thread and every vector of the block, so the inner loop is one shared gather per
-// (row, entry): ncu on the previous version (entries re-read from shared memory per row) showed 54 shared wavefronts and
-// 270 issued instructions per 32 rows, both near their limits (profiles/README_r02.md).
-template <class T>
-struct RegPattern {
-  T v[kWinRegs];
-  int32_t off[kWinRegs];
-  int32_t len;
-  __device__ __forceinline__ void load(const PatEntry<T>* __restrict__ pat, int32_t n, const WinShift& w) {
-    len = n;
-#pragma unroll
-    for (int q = 0; q < kWinRegs; ++q) {
-      v[q] = zeroOf<T>();
-      off[q] = 0;
-      if (q < n) {
-        const PatEntry<T> e = ldEntry<T>(pat + q);
-        v[q] = entryVal(e);
-        off[q] = w.of(e.d);
-      }
-    }
-  }
-  // NR rows of this thread: r[i] = r0 + i * stride; ascending column order, separately rounded multiply and add
-  template <int NR>
-  __device__ __forceinline__ void dot(const T* __restrict__ xs, int32_t r0, int32_t stride, T (&acc)[NR]) const {
-#pragma unroll
-    for (int i = 0; i < NR; ++i) acc[i] = zeroOf<T>();
-#pragma unroll
-    for (int q = 0; q < kWinRegs; ++q)
-      if (q < len) {
-        const T* px = xs + r0 + off[q];
-#pragma unroll
-        for (int i = 0; i < NR; ++i) accum(acc[i], v[q], px[i * stride]);
-      }
-  }
-};
-
-// per-lane fallback: entries from the global pattern table, x from the shared windows
+// one row: entries from `ent` (per-warp shared slot or the global pattern table), x from the shared windows; ascending
+// column order with separately rounded multiply and add, as everywhere in this file
 template <class T>
 __device__ __forceinline__ T winRowDot(const PatEntry<T>* __restrict__ ent, int32_t len, int32_t r, const T* __restrict__ xs, const WinShift& w) {
   T acc = zeroOf<T>();
@@ -302,21 +264,18 @@ __device__ __forceinline__ T winRowDot(const PatEntry<T>* __restrict__ ent, int3
   for (; q + 1 < len; q += 2) {
     const PatEntry<T> e0 = ldEntry<T>(ent + q);
     const PatEntry<T> e1 = ldEntry<T>(ent + q + 1);
-    const T x0 = xs[r + w.of(e0.d)];
-    const T x1 = xs[r + w.of(e1.d)];
+    const T x0 = xs[r + e0.d + (e0.d < w.dLo ? w.s0 : (e0.d > w.dHi ? w.s2 : w.s1))];
+    const T x1 = xs[r + e1.d + (e1.d < w.dLo ? w.s0 : (e1.d > w.dHi ? w.s2 : w.s1))];
     accum(acc, entryVal(e0), x0);
     accum(acc, entryVal(e1), x1);
   }
   if (q < len) {
     const PatEntry<T> e0 = ldEntry<T>(ent + q);
-    accum(acc, entryVal(e0), xs[r + w.of(e0.d)]);
+    accum(acc, entryVal(e0), xs[r + e0.d + (e0.d < w.dLo ? w.s0 : (e0.d > w.dHi ? w.s2 : w.s1))]);
   }
   return acc;
 }
 
-// ILV = 3: a warp owns 32 * RPT consecutive CELLS of one field component (lane l: cells l, l + 32, ...; rows are 3 apart
-// per cell, so one thread's rows are 96 apart and a warp reads the windows with stride 3 doubles: no bank conflict).
-// Three warps (components 0..2) cover a contiguous group of 96 * RPT rows. ILV = 1: lane l owns rows l, l + 32, ...
 template <class T, int ILV, int RPT>
 __global__ void __launch_bounds__(kWinThreads) k_spmm_win(int64_t rowBegin, int64_t rowEnd, int64_t tile0, DictArgs<T> D,
                                                           const WinTile* __restrict__ tiles, XSource<T> X, ColTable<T> Y, int nvec,
@@ -324,7 +283,9 @@ __global__ void __launch_bounds__(kWinThreads) k_spmm_win(int64_t rowBegin, int6
   extern __shared__ __align__(128) unsigned char smemRaw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smemRaw);
   WinTile* Ws = reinterpret_cast<WinTile*>(smemRaw + 64);
-  T* buf = reinterpret_cast<T*>(smemRaw + 128);
+  PatEntry<T>* slots = reinterpret_cast<PatEntry<T>*>(smemRaw + 128);
+  constexpr int kWarps = kWinThreads / 32;
+  T* buf = reinterpret_cast<T*>(smemRaw + 128 + sizeof(PatEntry<T>) * kWarps * RPT * kWinSlot);
   constexpr int R = kWinThreads * RPT;
   const int64_t tile = tile0 + blockIdx.x;
   if (threadIdx.x == 0) {
@@ -337,61 +298,44 @@ __global__ void __launch_bounds__(kWinThreads) k_spmm_win(int64_t rowBegin, int6
     if (Ws->valid) winIssue<T>(*Ws, X.x.p[0], buf, bar);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int rowStride = 32 * ILV;   // distance between a thread's consecutive rows
-  const int64_t row0 = tile * R + (ILV == 3 ? (warp / 3) * (96 * RPT) + 3 * lane + (warp % 3) : warp * (32 * RPT) + lane);
-  int32_t p[RPT], o[RPT], len[RPT];
+  const int tOff = ILV == 3 ? (warp / 3) * 96 + 3 * lane + (warp % 3) : int(threadIdx.x);
+  int64_t row[RPT];
+  int32_t o[RPT], len[RPT];
+  bool uni[RPT];
 #pragma unroll
   for (int i = 0; i < RPT; ++i) {
-    const int64_t row = row0 + i * rowStride;
-    p[i] = -1;
-    if (row >= rowBegin && row < rowEnd) p[i] = D.rowPat[row];
+    row[i] = tile * R + i * kWinThreads + tOff;
+    int32_t p = -1;
+    if (row[i] >= rowBegin && row[i] < rowEnd) p = D.rowPat[row[i]];
     o[i] = len[i] = 0;
-    if (p[i] >= 0) { o[i] = __ldg(D.patOff + p[i]); len[i] = __ldg(D.patOff + p[i] + 1) - o[i]; }
+    if (p >= 0) { o[i] = __ldg(D.patOff + p); len[i] = __ldg(D.patOff + p + 1) - o[i]; }
+    // warp-uniform pattern (lanes without a dictionary row do not count): stage its entries once for the whole warp
+    const int32_t pmax = __reduce_max_sync(0xffffffffu, p);
+    uni[i] = __all_sync(0xffffffffu, p < 0 || p == pmax) && pmax >= 0;
+    const int32_t oU = __shfl_sync(0xffffffffu, o[i], __ffs(__ballot_sync(0xffffffffu, p == pmax)) - 1);
+    const int32_t lenU = __shfl_sync(0xffffffffu, len[i], __ffs(__ballot_sync(0xffffffffu, p == pmax)) - 1);
+    uni[i] = uni[i] && lenU <= kWinSlot;
+    if (uni[i] && lane < lenU) slots[(warp * RPT + i) * kWinSlot + lane] = ldEntry<T>(D.pat + oU + lane);
   }
-  // one pattern for ALL rows of the warp? (every lane, every row slot: a lane without a dictionary row would read
-  // outside the staged windows, so such warps take the per-slot paths below)
-  const int32_t pmax = __shfl_sync(0xffffffffu, p[0], 0);
-  bool mine = pmax >= 0;
-#pragma unroll
-  for (int i = 0; i < RPT; ++i) mine = mine && p[i] == pmax;
-  const bool uniAll = __all_sync(0xffffffffu, mine) && len[0] <= kWinRegs;
-  const int32_t oU = o[0], lenU = len[0];
   __syncthreads();
   if (!Ws->valid) {   // tile-uniform: gather path
 #pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-      const int64_t row = row0 + i * rowStride;
-      if (row >= rowBegin && row < rowEnd) dictRow<T, false, 1>(row, D, X, Y, nvec, ep);
-    }
+    for (int i = 0; i < RPT; ++i)
+      if (row[i] >= rowBegin && row[i] < rowEnd) dictRow<T, false, 1>(row[i], D, X, Y, nvec, ep);
     return;
   }
-  const WinShift ws{Ws->dLo, Ws->dHi, Ws->shift[0], Ws->shift[1], Ws->shift[2]};
-  RegPattern<T> P;
-  if (uniAll) P.load(D.pat + oU, lenU, ws);
-  const T* __restrict__ xs = buf;
+  const int32_t dLo = Ws->dLo, dHi = Ws->dHi, s0 = Ws->shift[0], s1 = Ws->shift[1], s2 = Ws->shift[2];
   for (int j = 0; j < nvec; ++j) {
     mbarWait(bar, j & 1);
-    T* __restrict__ y = Y.p[j];
-    if (uniAll) {
-      T acc[RPT];
-      P.template dot<RPT>(xs, int32_t(row0), rowStride, acc);
+    const T* __restrict__ xs = buf;
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) storeY(y, row0 + i * rowStride, acc[i], ep);
-    } else {
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        // a z-line ends inside this warp's cells: row slots that are still uniform share one pattern
-        const int32_t pmx = __shfl_sync(0xffffffffu, p[i], 0);
-        const bool uni = __all_sync(0xffffffffu, p[i] == pmx && pmx >= 0) && len[i] <= kWinRegs;
-        if (uni) {
-          P.load(D.pat + o[i], len[i], ws);   // P is free here
-          T acc[1];
-          P.template dot<1>(xs, int32_t(row0 + i * rowStride), 0, acc);
-          storeY(y, row0 + i * rowStride, acc[0], ep);
-        } else if (len[i] > 0) {
-          storeY(y, row0 + i * rowStride, winRowDot<T>(D.pat + o[i], len[i], int32_t(row0 + i * rowStride), xs, ws), ep);
-        }
-      }
+    for (int i = 0; i < RPT; ++i) {
+      if (len[i] == 0) continue;
+      const int32_t r = int32_t(row[i]);
+      const WinShift ws{dLo, dHi, s0, s1, s2};
+      const T acc = uni[i] ? winRowDot<T>(slots + (warp * RPT + i) * kWinSlot, len[i], r, xs, ws)
+                           : winRowDot<T>(D.pat + o[i], len[i], r, xs, ws);
+      storeY(Y.p[j], row[i], acc, ep);
     }
     if (j + 1 < nvec) {
       __syncthreads();   // everyone is done with the windows of vector j
@@ -422,21 +366,30 @@ struct WaitArgs {
   const unsigned long long* epoch;
   int senderRank[8];
   int* err;
+  long long timeoutTicks;   // 0 = wait for ever (MXG_HALO_TIMEOUT_S, default 120 s)
 };
+// A neighbour that never publishes its epoch means a dead or dead-locked rank. Continuing would compute boundary rows
+// from stale ghost values and return wrong numbers with a success code, so the wait records the fault in the mapped
+// error word and traps: every later call on the context fails loudly.
+__device__ __forceinline__ void haloWait(const WaitArgs& W, int k) {
+  const unsigned long long e = *W.epoch;
+  const volatile unsigned long long* f = W.flags + W.senderRank[k];
+  const long long t0 = clock64();
+  while (*f < e) {
+    if (W.timeoutTicks > 0 && clock64() - t0 > W.timeoutTicks) {
+      *W.err = 1;
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+    __nanosleep(64);
+  }
+  __threadfence_system();
+}
 template <class T, bool GHOST, int NV>
 __global__ void __launch_bounds__(kBlock) k_spmm_multi(Segments G, DictArgs<T> D, SellArgs<T> S,
                                                        XSource<T> X, ColTable<T> Y, int nvec, Epilogue<T> ep, WaitArgs W) {
   if (GHOST && W.n > 0) {
-    if (threadIdx.x < W.n) {
-      const unsigned long long e = *W.epoch;
-      const volatile unsigned long long* f = W.flags + W.senderRank[threadIdx.x];
-      const long long t0 = clock64();
-      while (*f < e) {
-        if (clock64() - t0 > 4000000000ll) { *W.err = 1; break; }   // ~2 s: the neighbour is gone
-        __nanosleep(64);
-      }
-      __threadfence_system();
-    }
+    if (threadIdx.x < W.n) haloWait(W, threadIdx.x);
     __syncthreads();
   }
   if (GHOST && X.epoch) X.ghost += int64_t(*X.epoch & 1ull) * X.halfStride;
@@ -498,29 +451,30 @@ template <> struct WinCfg<zd> { static constexpr int RPT = 1; };
 constexpr size_t kWinSmemMax = 200 * 1024;      // per CTA
 constexpr size_t kWinBufBudget = 100 * 1024;    // one window set
 template <class T>
-constexpr size_t winSmemHeader() { return 128; }
-
-template <class T, int ILV, int RPT>
-int launchWinK(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, const XSource<T>& X, const ColTable<T>& Y, int nvec,
-               const Epilogue<T>& ep, cudaStream_t st) {
-  const int R = A->winR;
-  const int64_t tile0 = rowBegin / R, tiles = (rowEnd + R - 1) / R - tile0;
-  const size_t smem = winSmemHeader<T>() + size_t(A->winBufElems) * sizeof(T);
-  auto kern = k_spmm_win<T, ILV, RPT>;
-  static bool attrSet = false;
-  if (!attrSet) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWinSmemMax))); attrSet = true; }
-  kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, dictArgs<T>(A), static_cast<const WinTile*>(A->dWinTiles), X, Y, nvec, ep);
-  LAUNCH_CHECK(A->ctx);
-  return MXG_OK;
-}
+constexpr size_t winSmemHeader() { return 128 + sizeof(PatEntry<T>) * (kWinThreads / 32) * WinCfg<T>::RPT * kWinSlot; }
 
 template <class T>
 int launchWin(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, const XSource<T>& X, const ColTable<T>& Y, int nvec,
               const Epilogue<T>& ep, cudaStream_t st) {
+  mxg_ctx* ctx = A->ctx;
   constexpr int RPT = WinCfg<T>::RPT;
-  const bool big = A->winR == kWinThreads * 2 * RPT;   // MXG_WIN_RPT: twice the rows per tile
-  if (A->winIlv == 3) return big ? launchWinK<T, 3, 2 * RPT>(A, rowBegin, rowEnd, X, Y, nvec, ep, st) : launchWinK<T, 3, RPT>(A, rowBegin, rowEnd, X, Y, nvec, ep, st);
-  return big ? launchWinK<T, 1, 2 * RPT>(A, rowBegin, rowEnd, X, Y, nvec, ep, st) : launchWinK<T, 1, RPT>(A, rowBegin, rowEnd, X, Y, nvec, ep, st);
+  const int R = A->winR;
+  const int64_t tile0 = rowBegin / R, tiles = (rowEnd + R - 1) / R - tile0;
+  const size_t smem = winSmemHeader<T>() + size_t(A->winBufElems) * sizeof(T);
+  const DictArgs<T> D = dictArgs<T>(A);
+  const WinTile* wt = static_cast<const WinTile*>(A->dWinTiles);
+  static bool attrSet[2] = {false, false};
+  if (A->winIlv == 3) {
+    auto kern = k_spmm_win<T, 3, RPT>;
+    if (!attrSet[0]) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWinSmemMax))); attrSet[0] = true; }
+    kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, D, wt, X, Y, nvec, ep);
+  } else {
+    auto kern = k_spmm_win<T, 1, RPT>;
+    if (!attrSet[1]) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWinSmemMax))); attrSet[1] = true; }
+    kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, D, wt, X, Y, nvec, ep);
+  }
+  LAUNCH_CHECK(ctx);
+  return MXG_OK;
 }
 
 template <class T, bool GHOST>
@@ -534,7 +488,9 @@ int launchRange(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, int64_t genB
   // merged kernel (launchBoundary).
   const bool prof = ctx->profiling;
   if (prof) MXG_CUDA(cudaEventRecord(ctx->prof[1], ctx->stream));
-  if (A->dictRows > 0 && rowEnd > rowBegin && A->winR > 0) {
+  // The windowed kernel wins for single vectors (0.232 vs 0.262 ms on pillbox-256); for blocks the gather kernels share
+  // every pattern load between 4 vectors and stay ahead (profiles/README_r02.md), so they keep the block applies.
+  if (A->dictRows > 0 && rowEnd > rowBegin && A->winR > 0 && nvec <= A->winMaxVec) {
     const int rc = launchWin<T>(A, rowBegin, rowEnd, X, Y, nvec, ep, st);
     if (rc) return rc;
   } else if (A->dictRows > 0 && rowEnd > rowBegin) {
@@ -617,20 +573,11 @@ __global__ void __launch_bounds__(kBlock) k_pack_p2p(ColTable<T> x, const int32_
   }
 }
 
-// One warp waits until every neighbour has published this epoch (bounded spin; sets *err on timeout).
+// One warp waits until every neighbour has published this epoch (see haloWait for the timeout policy).
 // A separate tiny kernel on purpose: letting every boundary block spin instead keeps hundreds of blocks
 // resident while the interior rows want the SMs (measured: 0.22 ms vs 0.18 ms per apply at 2 GPUs).
 __global__ void k_wait(WaitArgs W) {
-  if (int(threadIdx.x) < W.n) {
-    const unsigned long long e = *W.epoch;
-    const volatile unsigned long long* f = W.flags + W.senderRank[threadIdx.x];
-    const long long t0 = clock64();
-    while (*f < e) {
-      if (clock64() - t0 > 4000000000ll) { *W.err = 1; break; }   // ~2 s: the neighbour is gone
-      __nanosleep(64);
-    }
-    __threadfence_system();
-  }
+  if (int(threadIdx.x) < W.n) haloWait(W, threadIdx.x);
 }
 
 template <class T>
@@ -671,6 +618,7 @@ int haloSequenceP2P(const mxg_crs* A, XSource<T> X, const ColTable<T>& Y, int nv
   W.flags = q.flags;
   W.epoch = q.epoch;
   W.err = ctx->dErr;
+  W.timeoutTicks = ctx->haloTimeoutTicks;
   for (int k = 0; k < P.n; ++k) W.senderRank[k] = P.senderRank[k];
   k_wait<<<1, 32, 0, ctx->commStream>>>(W);
   LAUNCH_CHECK(ctx);
@@ -1178,8 +1126,7 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
     const char* env = std::getenv("MXG_SPMV_WIN");
     const bool want = !(env && std::strcmp(env, "0") == 0);
     if (want && A->dictRows > 0 && nLoc + A->gLo + A->gHi < (int64_t(1) << 30)) {
-      int R = kWinThreads * WinCfg<T>::RPT;
-      if (const char* e2 = std::getenv("MXG_WIN_RPT")) { if (std::atoi(e2) == 2 * WinCfg<T>::RPT) R *= 2; }
+      constexpr int R = kWinThreads * WinCfg<T>::RPT;
       constexpr int align = 16 / int(sizeof(T)) > 0 ? 16 / int(sizeof(T)) : 1;
       const PatEntry<T>* pe = pat.data();
       int64_t maxTotal = 0, valid = 0;
@@ -1193,6 +1140,8 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
         A->winTiles = int64_t(tiles.size());
         A->winValid = valid;
         A->winBufElems = maxTotal;
+        A->winMaxVec = 1;
+        if (const char* mv = std::getenv("MXG_WIN_MAXVEC")) A->winMaxVec = std::atoi(mv);
         // thread -> row assignment: component triples (GID = comp + 3 cell) share patterns at distance 3, scalar fields at 1
         int64_t same1 = 0, same3 = 0;
         for (int64_t r = 0; r + 3 < nRows; ++r) {

@@ -54,6 +54,7 @@ class HostMVT : public mx::MultiVec<S> {
     return *this;
   }
   std::shared_ptr<Map> getMap() const { return map_; }
+  static constexpr bool kTimesMatInPlace = false;
   void setSeed(uint64_t s) { seed_ = s; }
   void swap(HostMVT& o) {
     std::swap(map_, o.map_);

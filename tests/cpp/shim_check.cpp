@@ -48,6 +48,19 @@ static int run() {
   A.apply(ones, y);
   y.norm2(nrm);
   if (std::fabs(nrm[0] - std::sqrt(5.0)) > 1e-14) return 6;
+  // successive MvRandom calls -- also on a Clone()d block -- draw independent numbers (Epetra's Random() advances its state)
+  MxAnasaziMV<Scalar> r1(map, 2);
+  r1.MvRandom();
+  std::unique_ptr<mx::MultiVec<Scalar>> r2(r1.Clone(2));
+  r2->MvRandom();
+  std::unique_ptr<mx::MultiVec<Scalar>> r1copy(r1.CloneCopy());
+  r1.MvRandom();
+  for (mx::MultiVec<Scalar>* other : {r2.get(), r1copy.get()}) {
+    std::unique_ptr<mx::MultiVec<Scalar>> diff(r1.CloneCopy());
+    diff->MvAddMv(Scalar(1.0), r1, Scalar(-1.0), *other);
+    diff->MvNorm(nrm);
+    if (!(nrm[0] > 1e-3 && nrm[1] > 1e-3)) return 7;
+  }
   return 0;
 }
 

@@ -131,7 +131,7 @@ def test_clone_view_copy_setblock_semantics(mx, ctx, cplx):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
-@pytest.mark.parametrize("k,b", [(1, 1), (3, 2), (8, 4), (20, 10), (36, 12), (13, 7)])
+@pytest.mark.parametrize("k,b", [(1, 1), (3, 2), (8, 4), (20, 10), (36, 12), (13, 7), (48, 48), (48, 33), (70, 50)])
 def test_trans_mv_and_times_mat_add_mv(mx, ctx, cplx, k, b):
     m = _map(mx, ctx)
     A, X = _rand(mx, m, k, cplx, 21), _rand(mx, m, b, cplx, 22)
@@ -150,8 +150,23 @@ def test_trans_mv_and_times_mat_add_mv(mx, ctx, cplx, k, b):
     assert rel_err(Y.to_host(), alpha * (Ah @ B) + beta * Yh) < 1e-13
     Y.MvTimesMatAddMv(1.0, A, B, 0.0)
     assert rel_err(Y.to_host(), Ah @ B) < 1e-13
-    with pytest.raises(mx.MxError):
-        A.MvTimesMatAddMv(1.0, A, np.eye(k), 0.0)            # aliasing is rejected
+    if cplx or k > 48:
+        with pytest.raises(mx.MxError):
+            A.MvTimesMatAddMv(1.0, A, np.eye(k), 0.0)        # complex / wide blocks: the result must not share columns with A
+    else:
+        # real: in-place right-multiplication of a basis block (a row chunk of A is complete in shared memory before
+        # those rows are written), also into a subset of A's own columns
+        C = rng.standard_normal((k, k))
+        A.MvTimesMatAddMv(1.0, A, C, 0.0)
+        assert rel_err(A.to_host(), Ah @ C) < 1e-13
+        if k >= 2:
+            Ah2 = A.to_host()
+            sub = A.CloneView([1, 0])
+            C2 = rng.standard_normal((k, 2))
+            sub.MvTimesMatAddMv(0.5, A, C2, 0.0)
+            want = Ah2.copy()
+            want[:, [1, 0]] = 0.5 * (Ah2 @ C2)
+            assert rel_err(A.to_host(), want) < 1e-13
 
 
 def test_views_feed_gram_products(mx, ctx):

@@ -209,6 +209,7 @@ def test_windowed_kernel_equals_gather_kernel(mx, ctx, orc, name, size, monkeypa
     kernels (MXG_SPMV_WIN=0) and the oracle, on grids large enough for many tiles; block applies and the fused epilogue."""
     sim = orc.pillbox(size)
     monkeypatch.setenv("MXG_SPMV_WIN", "1")
+    monkeypatch.setenv("MXG_WIN_MAXVEC", "128")          # default: windowed kernel for single vectors only
     Aw, op, rmap, cmap = gpu_matrix(mx, ctx, sim, name)
     monkeypatch.setenv("MXG_SPMV_WIN", "0")
     Ag, _, _, _ = gpu_matrix(mx, ctx, sim, name)
