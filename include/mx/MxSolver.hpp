@@ -351,6 +351,8 @@ struct MxSolverParams {
   // constrained solves (MxSolverT::setConstraint): relative accuracy of the inner projection solves
   double projTolInit = 1e-10;   // initial block
   double projTolW = 1e-2;       // preconditioned residuals, every iteration
+  int projMaxItersW = 0;        // cap on the inner iterations of those projections (0 = none): what a loose projection lets
+                                // through is caught by the re-projection of X below
   double projTolX = 1e-3;       // re-projection of the iterate when its constraint violation becomes visible
   double reprojectRatio = 0.05; // re-project X when violation > ratio * max(relative residual, tol)
 };
@@ -600,7 +602,7 @@ class MxSolverT {
         auto W = view(Sb, wc);
         if (T_) { timeit(res.tPrec, [&] { T_->Apply(*Ra, *W); }); res.applyPrec += na; }
         else *W = *Ra;
-        if (C_) { timeit(res.tProj, [&] { C_->project(*W, p_.projTolW); }); res.projections += na; }
+        if (C_) { timeit(res.tProj, [&] { C_->project(*W, p_.projTolW, p_.projMaxItersW); }); res.projections += na; }
         auto MW = view(MSb, wc);
         applyM(*W, *MW);
         // W <- W - X (X^T M W)
@@ -974,7 +976,7 @@ class MxDivProjector : public mx::Operator<Scalar>, public mx::Constraint<Scalar
     if (&x != &y) y2 = dynamic_cast<const MV&>(x);
     project(y, tol_);
   }
-  void project(mx::MultiVec<Scalar>& b, double tol) const override {
+  void project(mx::MultiVec<Scalar>& b, double tol, int maxIters = 0) const override {
     MV& b2 = dynamic_cast<MV&>(b);
     const int nb = b2.GetNumberVecs();
     ensure(b2, nb);
@@ -986,7 +988,7 @@ class MxDivProjector : public mx::Operator<Scalar>, public mx::Constraint<Scalar
     typename mx::BlockKrylov<Scalar>::Fn T;
     if (Ts_) T = [&](const MV& in, MV& out) { Ts_->Apply(in, out); };
     else T = [&](const MV& in, MV& out) { mx::check(mxg_crs_jacobi(S_, in.getRawMV(), out.getRawMV())); };
-    numLinIters += krylov_.pcg(A, T, psi1, psi2, tol, maxIters_);                            // (:903-913)
+    numLinIters += krylov_.pcg(A, T, psi1, psi2, tol, maxIters > 0 ? std::min(maxIters, maxIters_) : maxIters_);   // (:903-913)
     const double one[2] = {1.0, 0.0};
     mx::check(mxg_crs_apply_axpby(G_, one, psi2.getRawMV(), one, b2.getRawMV()));            // y = gradPsi psi2 + bWork (:919-921)
     // faces of zero area are invisible to M but gradPsi writes them: keep them at zero (zeroUnusedComponents, which the

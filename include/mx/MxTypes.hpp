@@ -108,8 +108,8 @@ template <class S>
 class Constraint {
  public:
   virtual ~Constraint() {}
-  // b <- P b in place; the inner solve reduces its residual by `tol`
-  virtual void project(MultiVec<S>& b, double tol) const = 0;
+  // b <- P b in place; the inner solve reduces its residual by `tol` or stops after maxIters iterations (0 = no cap)
+  virtual void project(MultiVec<S>& b, double tol, int maxIters = 0) const = 0;
   // out[j] = |D M b_j|_2 given Mb = M b (the reference's checkDivergences, MxMagWaveOp.cpp:1211-1234)
   virtual void violation(const MultiVec<S>& Mb, std::vector<double>& out) const = 0;
 };

@@ -31,6 +31,7 @@ typedef struct mxs_projection {
   double tol_x;           /* ... re-projection of the iterate (0 = 1e-3) */
   double reproject_ratio; /* re-project X when |D M x|/|M x| > ratio * max(relative residual, tol) (0 = 0.05) */
   int max_iters;          /* inner CG iteration cap (0 = 500) */
+  int max_iters_w;        /* cap for the per-iteration projections of the preconditioned residuals (0 = none) */
 } mxs_projection;
 
 void mxs_default_params(mxs_params* p);

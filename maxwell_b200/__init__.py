@@ -136,7 +136,7 @@ class Projection(C.Structure):
     """mxs_projection (include/mxsolver.h): the divergence-cleaning projection as an eigensolver constraint."""
     _fields_ = [("divB", C.c_void_p), ("gradPsi", C.c_void_p), ("scaLapl", C.c_void_p), ("sca_prec", C.c_void_p),
                 ("tol_init", C.c_double), ("tol_w", C.c_double), ("tol_x", C.c_double), ("reproject_ratio", C.c_double),
-                ("max_iters", C.c_int)]
+                ("max_iters", C.c_int), ("max_iters_w", C.c_int)]
 
 
 def load_solver():
@@ -666,6 +666,7 @@ class MxSolver:
             P.sca_prec = pr["sca_prec"].h if pr.get("sca_prec") is not None else None
             P.tol_init, P.tol_w, P.tol_x = float(pr.get("tol_init", 0)), float(pr.get("tol_w", 0)), float(pr.get("tol_x", 0))
             P.reproject_ratio, P.max_iters = float(pr.get("reproject_ratio", 0)), int(pr.get("max_iters", 0))
+            P.max_iters_w = int(pr.get("max_iters_w", 0))
             info = (C.c_int64 * 8)()
             viol = np.zeros(m)
             rc = self._S.mxs_lobpcg_projected(self.ctx.h, self.A.h, self.m_diag.h if self.m_diag is not None else None,

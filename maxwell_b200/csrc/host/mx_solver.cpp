@@ -56,6 +56,7 @@ void runLobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, const mx
     if (proj->tol_w > 0) q.projTolW = proj->tol_w;
     if (proj->tol_x > 0) q.projTolX = proj->tol_x;
     if (proj->reproject_ratio > 0) q.reprojectRatio = proj->reproject_ratio;
+    if (proj->max_iters_w > 0) q.projMaxItersW = proj->max_iters_w;
   }
   MxSolverResult r = solver.solve(Xmv);
   const int m = sp.blockSize;
