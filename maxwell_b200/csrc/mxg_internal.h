@@ -197,6 +197,8 @@ struct mxg_crs {
   // buffer over NVLink by the pack kernel, followed by an epoch flag; no NCCL call per apply.
   struct P2P {
     bool on = false;
+    bool fused = true;                      // whole apply in one launch (k_apply_fused) instead of the multi-kernel graph
+    unsigned long long hostEpoch = 0;       // exchanges enqueued so far (= the device epoch once they have run)
     int capCols = 0;
     void* ghost = nullptr;                  // [2][capCols][gTot] scalars, IPC-exported (double buffered by epoch parity)
     unsigned long long* flags = nullptr;    // [nranks] epochs written by the senders, IPC-exported

@@ -597,6 +597,138 @@ P2PArgs p2pArgs(const mxg_crs* A) {
   return P;
 }
 
+// ---- the whole multi-rank apply in ONE launch -------------------------------------------------------------------------------
+// Round 1 replayed a five-node graph (pack -> flag -> wait kernel -> boundary rows || interior rows) and measured ~100 us per
+// apply waiting on the neighbours at 8 GPUs for ~33 us of interior work (profiles/README_r01.md): every link of that chain
+// is a kernel with a 5-10 us floor. Here the roles are block ranges of one grid, in scheduling order:
+//   [pack]      lowest block ids, resident first: boundary values of x go straight into the neighbours' ghost buffers
+//               (NVLink stores), the last pack block publishes the epoch flag there
+//   [interior]  dictionary + sliced-ELL rows that need no ghost value
+//   [boundary]  highest block ids: wait for the neighbours' flags (they were written at the START of the neighbours' kernels),
+//               then the rows that read ghosts
+// A boundary block only ever waits for pack blocks of OTHER GPUs, which precede everything else in their grids, so the wait
+// cannot dead-lock. The epoch is a kernel argument (counted on the host, identical on all ranks), the ghost buffers are
+// double buffered by its parity. Reference call: the Epetra_Import inside Epetra_CrsMatrix::Apply (MxCrsMatrix.cpp:347-353).
+constexpr int kFusedBlock = 384;
+struct FusedPlan {
+  int nPack, nDict, nSell;            // blocks per role; boundary blocks follow
+  int64_t dictBegin, dictEnd, sellBegin, sellEnd;
+  int ilv;
+  unsigned long long epoch;
+};
+template <class T, int NV>
+__global__ void __launch_bounds__(kFusedBlock) k_apply_fused(FusedPlan F, P2PArgs P, const int32_t* __restrict__ sendIdx, int64_t sendTotal,
+                                                             unsigned long long* epochDev, unsigned int* done, int capCols, Segments G,
+                                                             DictArgs<T> D, SellArgs<T> S, XSource<T> X, ColTable<T> Y, int nvec,
+                                                             Epilogue<T> ep, WaitArgs W) {
+  int b = blockIdx.x;
+  if (b < F.nPack) {
+    const unsigned long long par = F.epoch & 1ull;
+    for (int j = 0; j < nvec; ++j) {
+      const T* __restrict__ c = X.x.p[j];
+      for (int64_t i = b * int64_t(kFusedBlock) + threadIdx.x; i < sendTotal; i += int64_t(F.nPack) * kFusedBlock) {
+        int k = 0;
+        while (k + 1 < P.n && i >= P.sendOffset[k] + P.sendCount[k]) ++k;
+        T* dst = static_cast<T*>(P.ghost[k]) + (int64_t(par) * capCols + j) * P.remoteGTot[k] + P.remoteStart[k] + (i - P.sendOffset[k]);
+        *dst = c[sendIdx[i]];
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (atomicAdd(done, 1u) == unsigned(F.nPack) - 1u) {
+        *done = 0u;
+        __threadfence_system();
+        for (int k = 0; k < P.n; ++k) *reinterpret_cast<volatile unsigned long long*>(P.flag[k]) = F.epoch;
+        *epochDev = F.epoch;
+        __threadfence_system();
+      }
+    }
+    return;
+  }
+  b -= F.nPack;
+  if (b < F.nDict) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = F.dictBegin + b * int64_t(kFusedBlock) + (F.ilv == 3 ? (warp / 3) * 96 + 3 * lane + (warp % 3) : int(threadIdx.x));
+    if (row < F.dictEnd) dictRow<T, false, NV>(row, D, X, Y, nvec, ep);
+    return;
+  }
+  b -= F.nDict;
+  if (b < F.nSell) {
+    const int64_t i = F.sellBegin + b * int64_t(kFusedBlock) + threadIdx.x;
+    if (i < F.sellEnd) sellRow<T, false, NV>(i, S, X, Y, nvec, ep);
+    return;
+  }
+  b -= F.nSell;
+  // boundary rows
+  if (threadIdx.x < W.n) {
+    const volatile unsigned long long* f = W.flags + W.senderRank[threadIdx.x];
+    const long long t0 = clock64();
+    while (*f < F.epoch) {
+      if (W.timeoutTicks > 0 && clock64() - t0 > W.timeoutTicks) {
+        *W.err = 1;
+        __threadfence_system();
+        asm volatile("trap;");
+      }
+      __nanosleep(32);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  int seg = 0;
+  while (seg < 3 && b >= G.blockStart[seg + 1]) ++seg;
+  const int64_t idx = G.begin[seg] + int64_t(b - G.blockStart[seg]) * kFusedBlock + threadIdx.x;
+  if (idx >= G.end[seg]) return;
+  if (seg < 2) dictRow<T, true, NV>(idx, D, X, Y, nvec, ep);
+  else sellRow<T, true, NV>(idx, S, X, Y, nvec, ep);
+}
+
+template <class T>
+int launchFused(const mxg_crs* A, XSource<T> X, const ColTable<T>& Y, int nvec, const Epilogue<T>& ep) {
+  mxg_ctx* ctx = A->ctx;
+  const auto& q = A->p2p;
+  const P2PArgs P = p2pArgs<T>(A);
+  FusedPlan F;
+  F.nPack = int(std::min<int64_t>(std::max<int64_t>(1, (A->sendTotal + kFusedBlock - 1) / kFusedBlock), 8));
+  F.dictBegin = A->dictRows > 0 ? A->intBegin : 0;
+  F.dictEnd = A->dictRows > 0 ? A->intEnd : 0;
+  F.sellBegin = A->genIntBegin;
+  F.sellEnd = A->genIntEnd;
+  F.nDict = int((F.dictEnd - F.dictBegin + kFusedBlock - 1) / kFusedBlock);
+  F.nSell = int((F.sellEnd - F.sellBegin + kFusedBlock - 1) / kFusedBlock);
+  F.ilv = A->ilv;
+  F.epoch = q.hostEpoch;
+  Segments G;
+  const int64_t bb[4] = {0, A->intEnd, 0, A->genIntEnd};
+  const int64_t ee[4] = {A->dictRows > 0 ? A->intBegin : 0, A->dictRows > 0 ? A->nRows : A->intEnd, A->genIntBegin, A->nGen};
+  int blocks = 0;
+  for (int sgm = 0; sgm < 4; ++sgm) {
+    G.begin[sgm] = bb[sgm];
+    G.end[sgm] = ee[sgm] > bb[sgm] ? ee[sgm] : bb[sgm];
+    G.blockStart[sgm] = blocks;
+    blocks += int((G.end[sgm] - G.begin[sgm] + kFusedBlock - 1) / kFusedBlock);
+  }
+  G.blockStart[4] = blocks;
+  X.halfStride = int64_t(q.capCols) * X.gTot;
+  X.ghost = static_cast<const T*>(q.ghost) + int64_t(F.epoch & 1ull) * X.halfStride;   // this epoch's half of the double buffer
+  X.epoch = nullptr;
+  WaitArgs W{};
+  W.n = P.n;
+  W.flags = q.flags;
+  W.epoch = q.epoch;
+  W.err = ctx->dErr;
+  W.timeoutTicks = ctx->haloTimeoutTicks;
+  for (int k = 0; k < P.n; ++k) W.senderRank[k] = P.senderRank[k];
+  const int grid = F.nPack + F.nDict + F.nSell + blocks;
+  const DictArgs<T> D = dictArgs<T>(A);
+  const SellArgs<T> S = sellArgs<T>(A);
+  if (nvec == 1) k_apply_fused<T, 1><<<grid, kFusedBlock, 0, ctx->stream>>>(F, P, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, G, D, S, X, Y, nvec, ep, W);
+  else if (nvec == 2) k_apply_fused<T, 2><<<grid, kFusedBlock, 0, ctx->stream>>>(F, P, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, G, D, S, X, Y, nvec, ep, W);
+  else k_apply_fused<T, 4><<<grid, kFusedBlock, 0, ctx->stream>>>(F, P, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, G, D, S, X, Y, nvec, ep, W);
+  LAUNCH_CHECK(ctx);
+  return MXG_OK;
+}
+
 // pack (remote stores) -> signal -> wait -> boundary rows on the communication stream || interior rows
 template <class T>
 int haloSequenceP2P(const mxg_crs* A, XSource<T> X, const ColTable<T>& Y, int nvec, const Epilogue<T>& ep) {
@@ -715,6 +847,10 @@ int applyImpl(const mxg_crs* A, const mxg_mv* x, mxg_mv* y, const Epilogue<T>& e
   X.halfStride = 0;
   ColTable<T> Y = tableOf<T>(y);
   if (!halo) return launchRange<T, false>(A, 0, A->nRows, 0, A->nGen, X, Y, nvec, ep);
+  if (A->p2p.on && nvec <= A->p2p.capCols) {
+    ++A->p2p.hostEpoch;   // one epoch per exchange, on every path, so the device counter and all ranks stay in step
+    if (A->p2p.fused && !ctx->profiling) return launchFused<T>(A, X, Y, nvec, ep);
+  }
 
   // The multi-rank apply is ~10 enqueues (pack, events, NCCL group, 2-6 kernels) for tens of
   // microseconds of GPU work, i.e. launch-bound. Capture it once per operand set and replay.
@@ -855,6 +991,10 @@ int setupP2P(mxg_crs* A, int64_t gTot) {
   MXG_CUDA(cudaFree(dflag));
   q.capCols = cap;
   q.on = opened == 1 && (gTot > 0 || A->sendTotal > 0);
+  {
+    const char* f = std::getenv("MXG_HALO_FUSED");   // 0: the multi-kernel graph of round 1
+    q.fused = !(f && std::strcmp(f, "0") == 0);
+  }
   return MXG_OK;
 }
 
