@@ -349,7 +349,7 @@ struct MxSolverParams {
   bool randomInit = true;  // MxSolver.cpp:62-64 starts from MvRandom
   bool profile = false;    // per-phase wall times (synchronises around each phase)
   // constrained solves (MxSolverT::setConstraint): relative accuracy of the inner projection solves
-  double projTolInit = 1e-10;   // initial block
+  double projTolInit = 1e-6;    // initial block (what it leaves is removed by the re-projections of X)
   double projTolW = 1e-2;       // preconditioned residuals, every iteration
   int projMaxItersW = 0;        // cap on the inner iterations of those projections (0 = none): what a loose projection lets
                                 // through is caught by the re-projection of X below

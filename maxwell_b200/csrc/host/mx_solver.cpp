@@ -47,7 +47,7 @@ void runLobpcg(mxg_ctx* ctx, mxg_crs* A, mxg_mv* m_diag, mxg_gmg* prec, const mx
   if (proj) {
     if (proj->sca_prec) Tsca.reset(new MxGeoMultigridPrec<Scalar>(proj->sca_prec, false));
     P.reset(new MxDivProjector<Scalar>(proj->divB, proj->gradPsi, proj->scaLapl, m_diag, Tsca.get(), w.comm,
-                                       proj->tol_init > 0 ? proj->tol_init : 1e-10, proj->max_iters > 0 ? proj->max_iters : 500));
+                                       proj->tol_init > 0 ? proj->tol_init : 1e-6, proj->max_iters > 0 ? proj->max_iters : 500));
     solver.setConstraint(P.get());
   }
   if (proj) {

@@ -1180,7 +1180,11 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
   std::vector<int32_t> rowPat(nRows, -1);
   std::vector<int32_t> patOff(1, 0);
   std::vector<PatEntry<T>> pat;
-  if (layout != 1) {
+  // Rectangular operators on two different maps (div, grad, curl, the multigrid transfers) have no translation-invariant
+  // rows -- column minus row index drifts with the row -- so the dictionary pass would hash tens of millions of unique
+  // rows for nothing: they go straight to sliced ELL.
+  const bool sameMaps = A->rowMap == A->domMap || A->rowMap->gids == A->domMap->gids;
+  if (layout != 1 && sameMaps) {
     std::unordered_map<uint64_t, std::vector<int32_t>> table;  // hash -> candidate pattern ids
     table.reserve(1 << 16);
     struct Cand { int64_t row; int32_t count; };
