@@ -624,14 +624,14 @@ __global__ void __launch_bounds__(kFusedBlock) k_apply_fused(FusedPlan F, P2PArg
   int b = blockIdx.x;
   if (b < F.nPack) {
     const unsigned long long par = F.epoch & 1ull;
-    for (int j = 0; j < nvec; ++j) {
-      const T* __restrict__ c = X.x.p[j];
-      for (int64_t i = b * int64_t(kFusedBlock) + threadIdx.x; i < sendTotal; i += int64_t(F.nPack) * kFusedBlock) {
-        int k = 0;
-        while (k + 1 < P.n && i >= P.sendOffset[k] + P.sendCount[k]) ++k;
-        T* dst = static_cast<T*>(P.ghost[k]) + (int64_t(par) * capCols + j) * P.remoteGTot[k] + P.remoteStart[k] + (i - P.sendOffset[k]);
-        *dst = c[sendIdx[i]];
-      }
+    const int64_t total = sendTotal * nvec;
+    for (int64_t e = b * int64_t(kFusedBlock) + threadIdx.x; e < total; e += int64_t(F.nPack) * kFusedBlock) {
+      const int j = int(e / sendTotal);
+      const int64_t i = e - int64_t(j) * sendTotal;
+      int k = 0;
+      while (k + 1 < P.n && i >= P.sendOffset[k] + P.sendCount[k]) ++k;
+      T* dst = static_cast<T*>(P.ghost[k]) + (int64_t(par) * capCols + j) * P.remoteGTot[k] + P.remoteStart[k] + (i - P.sendOffset[k]);
+      *dst = X.x.p[j][sendIdx[i]];
     }
     __threadfence_system();
     __syncthreads();
@@ -689,7 +689,9 @@ int launchFused(const mxg_crs* A, XSource<T> X, const ColTable<T>& Y, int nvec, 
   const auto& q = A->p2p;
   const P2PArgs P = p2pArgs<T>(A);
   FusedPlan F;
-  F.nPack = int(std::min<int64_t>(std::max<int64_t>(1, (A->sendTotal + kFusedBlock - 1) / kFusedBlock), 8));
+  // enough pack blocks that every thread moves a handful of values: the pack (remote NVLink stores) gates the neighbours'
+  // boundary rows, 8 blocks made it ~100 us long at 2 GPUs (profiles/README_r02.md)
+  F.nPack = int(std::min<int64_t>(std::max<int64_t>(1, (A->sendTotal * nvec + 2 * kFusedBlock - 1) / (2 * kFusedBlock)), ctx->numSMs));
   F.dictBegin = A->dictRows > 0 ? A->intBegin : 0;
   F.dictEnd = A->dictRows > 0 ? A->intEnd : 0;
   F.sellBegin = A->genIntBegin;
