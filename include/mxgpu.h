@@ -191,6 +191,11 @@ int mxg_crs_apply_axpby(const mxg_crs* A, const double alpha[2], const mxg_mv* x
 /* one apply with CUDA events around each kernel class: ms[0] = dictionary-row kernel,
  * ms[1] = sliced-ELL kernel, ms[2] = halo pack + exchange wait, ms[3] = whole apply */
 int mxg_crs_apply_timed(const mxg_crs* A, const mxg_mv* x, mxg_mv* y, double ms[4]);
+/* %globaltimer timeline of ONE multi-rank apply (the single-launch path): call with enable = 1, apply once, call with
+ * enable = 0 to read out[10] in ns relative to the earliest mark -- role r: out[2r] first start, out[2r+1] last end;
+ * roles: 0 pack + flag publish, 1 interior dictionary rows, 2 interior sliced-ELL rows, 3 boundary blocks waiting for the
+ * neighbours' flags, 4 boundary rows. Entries of roles that did not run are -1. */
+int mxg_crs_trace(const mxg_crs* A, int enable, double out[10]);
 /* layout statistics: out[0]=local rows, [1]=local nnz, [2]=rows on the dictionary path,
  * [3]=distinct row patterns, [4]=device bytes of the matrix layout, [5]=ghost entries,
  * [6]=rows that need ghosts, [7]=padded ELL entries */

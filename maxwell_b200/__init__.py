@@ -97,6 +97,7 @@ def load_library():
         "mxg_crs_apply_host_batch": (i32, [vp, i32, vp, vp]),
         "mxg_crs_apply_axpby": (i32, [vp, dp, vp, dp, vp]),
         "mxg_crs_stats": (i32, [vp, vp]),
+        "mxg_crs_trace": (i32, [vp, i32, vp]),
         "mxg_mv_get_map": (vp, [vp]),
         "mxg_crs_row_map": (vp, [vp]),
         "mxg_crs_domain_map": (vp, [vp]),
@@ -532,6 +533,15 @@ class MxCrsMatrix:
         ms = (C.c_double * 4)()
         _ck(self._L.mxg_crs_apply_timed(self.h, x.h, y.h, ms))
         return {"dict_ms": ms[0], "sell_ms": ms[1], "pre_ms": ms[2], "total_ms": ms[3]}
+
+    def trace_apply(self, x, y):
+        """One multi-rank apply with %globaltimer marks: ns since the first mark for pack / interior / boundary roles."""
+        out = (C.c_double * 10)()
+        _ck(self._L.mxg_crs_trace(self.h, 1, out))
+        self.apply(x, y)
+        _ck(self._L.mxg_crs_trace(self.h, 0, out))
+        names = ["pack", "interior_dict", "interior_sell", "boundary_wait", "boundary_rows"]
+        return {n: (out[2 * i], out[2 * i + 1]) for i, n in enumerate(names)}
 
     def stats(self):
         out = (C.c_int64 * 8)()

@@ -182,6 +182,7 @@ struct mxg_crs {
   void* dWinTiles = nullptr;           // WinTile[winTiles]
   int winR = 0;                        // rows per tile (0 = windowed path off)
   int winIlv = 1;                      // thread -> row assignment inside a tile (1 or 3)
+  int winKernel = 0;                   // 0: one tile per CTA (entries in shared slots), 1: persistent pipelined CTAs (entries in registers)
   int winMaxVec = 1;                   // widest block the windowed kernel takes (wider blocks: gather kernels)
   int64_t winTiles = 0, winValid = 0;  // tiles / tiles served from shared memory
   int64_t winBufElems = 0;             // largest window set of any tile (scalars)
@@ -204,6 +205,7 @@ struct mxg_crs {
     unsigned long long* flags = nullptr;    // [nranks] epochs written by the senders, IPC-exported
     unsigned long long* epoch = nullptr;    // local apply counter
     unsigned int* done = nullptr;           // block-completion counter of the pack kernel
+    unsigned long long* trace = nullptr;    // %globaltimer marks of the fused apply (mxg_crs_trace), NULL = off
     int npeers = 0;
     int peerRank[8];
     void* peerGhost[8];

@@ -444,6 +444,187 @@ int launchSegments(const mxg_crs* A, const int64_t b[4], const int64_t e[4], con
 }
 
 
+// ---- persistent, pipelined variant of the windowed kernel --------------------------------------------------------------------
+// Two lessons from the versions above (ncu, profiles/README_r02.md): (i) re-reading the pattern entries from shared memory for
+// every row costs as many load wavefronts as the x gathers themselves -- keep them in REGISTERS (RegPattern): a warp owns
+// 32 * RPT consecutive cells of one field component, which share a pattern inside a z-line, so one set of <= 14
+// (value, shared-offset) pairs serves RPT rows per lane and every vector of a block; (ii) that costs ~80 registers, i.e. two
+// 384-thread CTAs per SM, which is too little to hide a TMA round trip per tile -- so the CTA is PERSISTENT and prefetches:
+// a ring of STAGES window buffers, thread 0 issues the bulk copies of work item m + STAGES as soon as item m's buffer is
+// released. A work item is (tile, vector): block applies stream the columns through the same ring.
+constexpr int kWinRegs = 14;   // pattern entries kept in registers (longer rows take the per-lane path)
+struct WinShift2 {
+  int32_t dLo, dHi, s0, s1, s2;
+  __device__ __forceinline__ int32_t of(int32_t d) const { return d + (d < dLo ? s0 : (d > dHi ? s2 : s1)); }
+};
+template <class T>
+struct RegPattern {
+  T v[kWinRegs];
+  int32_t off[kWinRegs];
+  int32_t len;
+  __device__ __forceinline__ void load(const PatEntry<T>* __restrict__ pat, int32_t n, const WinShift2& w) {
+    len = n;
+#pragma unroll
+    for (int q = 0; q < kWinRegs; ++q) {
+      v[q] = zeroOf<T>();
+      off[q] = 0;
+      if (q < n) {
+        const PatEntry<T> e = ldEntry<T>(pat + q);
+        v[q] = entryVal(e);
+        off[q] = w.of(e.d);
+      }
+    }
+  }
+  // NR rows of this thread, r0 + i * stride; ascending column order, separately rounded multiply and add
+  template <int NR>
+  __device__ __forceinline__ void dot(const T* __restrict__ xs, int32_t r0, int32_t stride, T (&acc)[NR]) const {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) acc[i] = zeroOf<T>();
+#pragma unroll
+    for (int q = 0; q < kWinRegs; ++q)
+      if (q < len) {
+        const T* px = xs + r0 + off[q];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) accum(acc[i], v[q], px[i * stride]);
+      }
+  }
+};
+template <class T>
+__device__ __forceinline__ T winRowDot2(const PatEntry<T>* __restrict__ ent, int32_t len, int32_t r, const T* __restrict__ xs, const WinShift2& w) {
+  T acc = zeroOf<T>();
+  for (int32_t q = 0; q < len; ++q) {
+    const PatEntry<T> e0 = ldEntry<T>(ent + q);
+    accum(acc, entryVal(e0), xs[r + w.of(e0.d)]);
+  }
+  return acc;
+}
+
+template <class T, int ILV, int RPT, int STAGES>
+__global__ void __launch_bounds__(kWinThreads, 2) k_spmm_winp(int64_t rowBegin, int64_t rowEnd, int64_t tile0, int64_t nTiles, DictArgs<T> D,
+                                                              const WinTile* __restrict__ tiles, int bufElems, XSource<T> X, ColTable<T> Y,
+                                                              int nvec, Epilogue<T> ep) {
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smemRaw);          // STAGES barriers
+  T* buf = reinterpret_cast<T*>(smemRaw + 128);
+  constexpr int R = kWinThreads * RPT;
+  // this CTA's tiles: blockIdx.x, blockIdx.x + gridDim.x, ...; work item m = (tile m / nvec, vector m % nvec)
+  const int64_t nMine = (nTiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int64_t nItems = nMine * nvec;
+  auto issue = [&](int64_t m) {   // thread 0 only
+    const int64_t tile = tile0 + blockIdx.x + (m / nvec) * gridDim.x;
+    const int s = int(m % STAGES);
+    const WinTile* W = tiles + tile;
+    if (__ldg(&W->valid)) {
+      uint32_t bytes = 0;
+      int32_t lo[3], ln[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { lo[k] = __ldg(&W->segLo[k]); ln[k] = __ldg(&W->segLen[k]); bytes += uint32_t(ln[k]) * uint32_t(sizeof(T)); }
+      mbarExpectTx(&bar[s], bytes);
+      const T* xcol = X.x.p[int(m % nvec)];
+      int off = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (ln[k] > 0) bulkLoad(buf + int64_t(s) * bufElems + off, xcol + lo[k], uint32_t(ln[k]) * uint32_t(sizeof(T)), &bar[s]);
+        off += ln[k];
+      }
+    } else {
+      mbarExpectTx(&bar[s], 0);   // gather-path tile: nothing to stage, complete the phase
+    }
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbarInit(&bar[s], 1);
+    mbarFenceInit();
+    for (int64_t m = 0; m < STAGES && m < nItems; ++m) issue(m);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int rowStride = 32 * ILV;
+  const int tOff = ILV == 3 ? (warp / 3) * (96 * RPT) + 3 * lane + (warp % 3) : warp * (32 * RPT) + lane;
+  RegPattern<T> P;
+  int32_t p[RPT], o[RPT], len[RPT];
+  bool uniAll = false, valid = false;
+  WinShift2 ws{0, 0, 0, 0, 0};
+  int64_t row0 = 0;
+  for (int64_t m = 0; m < nItems; ++m) {
+    const int j = int(m % nvec);
+    const int s = int(m % STAGES);
+    if (j == 0) {   // new tile: row patterns
+      const int64_t tile = tile0 + blockIdx.x + (m / nvec) * gridDim.x;
+      const WinTile* W = tiles + tile;
+      valid = __ldg(&W->valid) != 0;
+      ws = WinShift2{__ldg(&W->dLo), __ldg(&W->dHi), __ldg(&W->shift[0]), __ldg(&W->shift[1]), __ldg(&W->shift[2])};
+      row0 = tile * R + tOff;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int64_t row = row0 + i * rowStride;
+        p[i] = -1;
+        if (row >= rowBegin && row < rowEnd) p[i] = D.rowPat[row];
+        o[i] = len[i] = 0;
+        if (p[i] >= 0) { o[i] = __ldg(D.patOff + p[i]); len[i] = __ldg(D.patOff + p[i] + 1) - o[i]; }
+      }
+      const int32_t p0 = __shfl_sync(0xffffffffu, p[0], 0);
+      bool mine = p0 >= 0;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) mine = mine && p[i] == p0;
+      uniAll = valid && __all_sync(0xffffffffu, mine) && len[0] <= kWinRegs;
+      if (uniAll) P.load(D.pat + o[0], len[0], ws);
+    }
+    mbarWait(&bar[s], uint32_t((m / STAGES) & 1));
+    if (!valid) {
+      if (j == 0) {
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int64_t row = row0 + i * rowStride;
+          if (row >= rowBegin && row < rowEnd) dictRow<T, false, 1>(row, D, X, Y, nvec, ep);   // all vectors at once
+        }
+      }
+    } else {
+      const T* __restrict__ xs = buf + int64_t(s) * bufElems;
+      T* __restrict__ y = Y.p[j];
+      if (uniAll) {
+        T acc[RPT];
+        P.template dot<RPT>(xs, int32_t(row0), rowStride, acc);
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) storeY(y, row0 + i * rowStride, acc[i], ep);
+      } else {
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int32_t pi0 = __shfl_sync(0xffffffffu, p[i], 0);
+          const bool uni = __all_sync(0xffffffffu, p[i] == pi0 && pi0 >= 0) && len[i] <= kWinRegs;
+          if (uni) {     // a z-line ends elsewhere in this warp's cells, this row slot is still uniform
+            P.load(D.pat + o[i], len[i], ws);
+            T acc[1];
+            P.template dot<1>(xs, int32_t(row0 + i * rowStride), 0, acc);
+            storeY(y, row0 + i * rowStride, acc[0], ep);
+          } else if (len[i] > 0) {
+            storeY(y, row0 + i * rowStride, winRowDot2<T>(D.pat + o[i], len[i], int32_t(row0 + i * rowStride), xs, ws), ep);
+          }
+        }
+      }
+    }
+    __syncthreads();                                       // stage s is free again
+    if (threadIdx.x == 0 && m + STAGES < nItems) issue(m + STAGES);
+  }
+}
+
+template <class T, int ILV, int RPT>
+int launchWinP(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, const XSource<T>& X, const ColTable<T>& Y, int nvec,
+               const Epilogue<T>& ep, cudaStream_t st) {
+  constexpr int STAGES = 2;
+  const int R = A->winR;
+  const int64_t tile0 = rowBegin / R, tiles = (rowEnd + R - 1) / R - tile0;
+  const size_t smem = 128 + size_t(STAGES) * size_t(A->winBufElems) * sizeof(T);
+  auto kern = k_spmm_winp<T, ILV, RPT, STAGES>;
+  static bool attrSet = false;
+  if (!attrSet) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attrSet = true; }
+  const int grid = int(std::min<int64_t>(tiles, int64_t(A->ctx->numSMs) * (2 * smem + 2048 <= 227 * 1024 ? 2 : 1)));
+  kern<<<grid, kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, tiles, dictArgs<T>(A), static_cast<const WinTile*>(A->dWinTiles),
+                                         int(A->winBufElems), X, Y, nvec, ep);
+  LAUNCH_CHECK(A->ctx);
+  return MXG_OK;
+}
+
 // rows per thread of the windowed kernel (tile = kWinThreads * RPT rows)
 template <class T> struct WinCfg;
 template <> struct WinCfg<double> { static constexpr int RPT = 2; };
@@ -458,6 +639,9 @@ int launchWin(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, const XSource<
               const Epilogue<T>& ep, cudaStream_t st) {
   mxg_ctx* ctx = A->ctx;
   constexpr int RPT = WinCfg<T>::RPT;
+  if (A->winKernel == 1 && 128 + 2 * size_t(A->winBufElems) * sizeof(T) <= 110 * 1024) {
+    return A->winIlv == 3 ? launchWinP<T, 3, RPT>(A, rowBegin, rowEnd, X, Y, nvec, ep, st) : launchWinP<T, 1, RPT>(A, rowBegin, rowEnd, X, Y, nvec, ep, st);
+  }
   const int R = A->winR;
   const int64_t tile0 = rowBegin / R, tiles = (rowEnd + R - 1) / R - tile0;
   const size_t smem = winSmemHeader<T>() + size_t(A->winBufElems) * sizeof(T);
@@ -615,7 +799,21 @@ struct FusedPlan {
   int64_t dictBegin, dictEnd, sellBegin, sellEnd;
   int ilv;
   unsigned long long epoch;
+  unsigned long long* trace;          // optional %globaltimer timeline (mxg_crs_trace): [2 role] = min start, [2 role + 1] = max end
 };
+__device__ __forceinline__ unsigned long long globalTimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// roles: 0 pack, 1 interior dictionary rows, 2 interior sliced-ELL rows, 3 boundary wait, 4 boundary rows
+__device__ __forceinline__ void traceMark(unsigned long long* trace, int role, bool end) {
+  if (trace && threadIdx.x == 0) {
+    const unsigned long long t = globalTimer();
+    if (end) atomicMax(trace + 2 * role + 1, t);
+    else atomicMin(trace + 2 * role, t);
+  }
+}
 template <class T, int NV>
 __global__ void __launch_bounds__(kFusedBlock) k_apply_fused(FusedPlan F, P2PArgs P, const int32_t* __restrict__ sendIdx, int64_t sendTotal,
                                                              unsigned long long* epochDev, unsigned int* done, int capCols, Segments G,
@@ -623,6 +821,7 @@ __global__ void __launch_bounds__(kFusedBlock) k_apply_fused(FusedPlan F, P2PArg
                                                              Epilogue<T> ep, WaitArgs W) {
   int b = blockIdx.x;
   if (b < F.nPack) {
+    traceMark(F.trace, 0, false);
     const unsigned long long par = F.epoch & 1ull;
     const int64_t total = sendTotal * nvec;
     for (int64_t e = b * int64_t(kFusedBlock) + threadIdx.x; e < total; e += int64_t(F.nPack) * kFusedBlock) {
@@ -644,23 +843,29 @@ __global__ void __launch_bounds__(kFusedBlock) k_apply_fused(FusedPlan F, P2PArg
         __threadfence_system();
       }
     }
+    traceMark(F.trace, 0, true);
     return;
   }
   b -= F.nPack;
   if (b < F.nDict) {
+    traceMark(F.trace, 1, false);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = F.dictBegin + b * int64_t(kFusedBlock) + (F.ilv == 3 ? (warp / 3) * 96 + 3 * lane + (warp % 3) : int(threadIdx.x));
     if (row < F.dictEnd) dictRow<T, false, NV>(row, D, X, Y, nvec, ep);
+    if (F.trace) { __syncthreads(); traceMark(F.trace, 1, true); }
     return;
   }
   b -= F.nDict;
   if (b < F.nSell) {
+    traceMark(F.trace, 2, false);
     const int64_t i = F.sellBegin + b * int64_t(kFusedBlock) + threadIdx.x;
     if (i < F.sellEnd) sellRow<T, false, NV>(i, S, X, Y, nvec, ep);
+    if (F.trace) { __syncthreads(); traceMark(F.trace, 2, true); }
     return;
   }
   b -= F.nSell;
   // boundary rows
+  traceMark(F.trace, 3, false);
   if (threadIdx.x < W.n) {
     const volatile unsigned long long* f = W.flags + W.senderRank[threadIdx.x];
     const long long t0 = clock64();
@@ -675,12 +880,16 @@ __global__ void __launch_bounds__(kFusedBlock) k_apply_fused(FusedPlan F, P2PArg
     __threadfence_system();
   }
   __syncthreads();
+  traceMark(F.trace, 3, true);
+  traceMark(F.trace, 4, false);
   int seg = 0;
   while (seg < 3 && b >= G.blockStart[seg + 1]) ++seg;
   const int64_t idx = G.begin[seg] + int64_t(b - G.blockStart[seg]) * kFusedBlock + threadIdx.x;
-  if (idx >= G.end[seg]) return;
-  if (seg < 2) dictRow<T, true, NV>(idx, D, X, Y, nvec, ep);
-  else sellRow<T, true, NV>(idx, S, X, Y, nvec, ep);
+  if (idx < G.end[seg]) {
+    if (seg < 2) dictRow<T, true, NV>(idx, D, X, Y, nvec, ep);
+    else sellRow<T, true, NV>(idx, S, X, Y, nvec, ep);
+  }
+  if (F.trace) { __syncthreads(); traceMark(F.trace, 4, true); }
 }
 
 template <class T>
@@ -700,6 +909,7 @@ int launchFused(const mxg_crs* A, XSource<T> X, const ColTable<T>& Y, int nvec, 
   F.nSell = int((F.sellEnd - F.sellBegin + kFusedBlock - 1) / kFusedBlock);
   F.ilv = A->ilv;
   F.epoch = q.hostEpoch;
+  F.trace = q.trace;
   Segments G;
   const int64_t bb[4] = {0, A->intEnd, 0, A->genIntEnd};
   const int64_t ee[4] = {A->dictRows > 0 ? A->intBegin : 0, A->dictRows > 0 ? A->nRows : A->intEnd, A->genIntBegin, A->nGen};
@@ -1287,6 +1497,7 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
         A->winValid = valid;
         A->winBufElems = maxTotal;
         A->winMaxVec = 1;
+        if (const char* wk = std::getenv("MXG_WIN_KERNEL")) A->winKernel = std::strcmp(wk, "p") == 0 ? 1 : 0;
         if (const char* mv = std::getenv("MXG_WIN_MAXVEC")) A->winMaxVec = std::atoi(mv);
         // thread -> row assignment: component triples (GID = comp + 3 cell) share patterns at distance 3, scalar fields at 1
         int64_t same1 = 0, same3 = 0;
@@ -1439,6 +1650,7 @@ int mxg_crs_destroy(mxg_crs* A) {
   if (A->p2p.flags) cudaFree(A->p2p.flags);
   if (A->p2p.epoch) cudaFree(A->p2p.epoch);
   if (A->p2p.done) cudaFree(A->p2p.done);
+  if (A->p2p.trace) cudaFree(A->p2p.trace);
   void* ptrs[] = {A->dRowPat, A->dPatOff, A->dPat, A->dGenRow, A->dGenLen, A->dSlicePtr, A->dCol, A->dVal, A->dSendIdx, A->dSendBuf, A->dGhost, A->dInvDiag, A->dWinTiles};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -1573,6 +1785,38 @@ int mxg_crs_apply_timed(const mxg_crs* A, const mxg_mv* x, mxg_mv* y, double ms[
     MXG_CUDA(cudaEventElapsedTime(&f, ctx->prof[1], ctx->prof[2])); ms[2] = f;   // NCCL send/recv
   }
   MXG_CUDA(cudaEventElapsedTime(&f, ctx->prof[0], ctx->prof[4])); ms[3] = f;
+  return MXG_OK;
+}
+
+// %globaltimer timeline of the fused multi-rank apply. enable != 0: arm (allocate / reset) the trace buffer; enable == 0:
+// read it back into out[10] (ns relative to the earliest mark; role r: out[2r] = first start, out[2r+1] = last end; roles:
+// 0 pack + publish, 1 interior dictionary rows, 2 interior sliced-ELL rows, 3 boundary blocks waiting for the neighbours'
+// flags, 4 boundary rows) and disarm.
+int mxg_crs_trace(const mxg_crs* A, int enable, double out[10]) {
+  MXG_REQUIRE(A, "mxg_crs_trace: NULL argument");
+  mxg_ctx* ctx = A->ctx;
+  MXG_CUDA(cudaSetDevice(ctx->device));
+  auto& q = A->p2p;
+  unsigned long long init[10];
+  for (int r = 0; r < 5; ++r) { init[2 * r] = ~0ull; init[2 * r + 1] = 0ull; }
+  if (enable) {
+    if (!q.trace) MXG_CUDA(cudaMalloc(&q.trace, sizeof(init)));
+    MXG_CUDA(cudaMemcpyAsync(q.trace, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    MXG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MXG_OK;
+  }
+  MXG_REQUIRE(q.trace && out, "mxg_crs_trace: trace not armed");
+  unsigned long long h[10];
+  MXG_CUDA(cudaStreamSynchronize(ctx->stream));
+  MXG_CUDA(cudaMemcpy(h, q.trace, sizeof(h), cudaMemcpyDeviceToHost));
+  unsigned long long t0 = ~0ull;
+  for (int r = 0; r < 5; ++r) if (h[2 * r] < t0) t0 = h[2 * r];
+  for (int r = 0; r < 5; ++r) {
+    out[2 * r] = h[2 * r] == ~0ull ? -1.0 : double(h[2 * r] - t0);
+    out[2 * r + 1] = h[2 * r + 1] == 0ull ? -1.0 : double(h[2 * r + 1] - t0);
+  }
+  MXG_CUDA(cudaFree(q.trace));
+  q.trace = nullptr;
   return MXG_OK;
 }
 

@@ -33,11 +33,12 @@ field = "psifield" if args.op == "scaLapl" else "bfield"
 bmap = mx.MxMap(ctx, sim.num_global(field), rg)
 cols = cg[col]
 ENV = {"gather": {"MXG_SPMV_WIN": "0"}, "win3": {"MXG_SPMV_WIN": "1", "MXG_SPMV_ILV": "3"}, "win1": {"MXG_SPMV_WIN": "1", "MXG_SPMV_ILV": "1"},
-       "win": {"MXG_SPMV_WIN": "1"}, "win4": {"MXG_SPMV_WIN": "1", "MXG_WIN_RPT": "4"}}
+       "win": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "t"}, "winmv": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "t", "MXG_WIN_MAXVEC": "128"},
+       "winp": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "p"}, "winpmv": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "p", "MXG_WIN_MAXVEC": "128"}}
 ref = {}
 out = {}
 for name in args.variants.split(","):
-    for k in ("MXG_SPMV_WIN", "MXG_SPMV_ILV", "MXG_WIN_RPT"):
+    for k in ("MXG_SPMV_WIN", "MXG_SPMV_ILV", "MXG_WIN_KERNEL", "MXG_WIN_MAXVEC"):
         os.environ.pop(k, None)
     os.environ.update(ENV[name])
     t = time.time()
