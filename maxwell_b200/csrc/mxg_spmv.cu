@@ -900,7 +900,7 @@ int launchFused(const mxg_crs* A, XSource<T> X, const ColTable<T>& Y, int nvec, 
   FusedPlan F;
   // enough pack blocks that every thread moves a handful of values: the pack (remote NVLink stores) gates the neighbours'
   // boundary rows, 8 blocks made it ~100 us long at 2 GPUs (profiles/README_r02.md)
-  F.nPack = int(std::min<int64_t>(std::max<int64_t>(1, (A->sendTotal * nvec + 2 * kFusedBlock - 1) / (2 * kFusedBlock)), ctx->numSMs));
+  F.nPack = A->sendTotal == 0 ? 0 : int(std::min<int64_t>(std::max<int64_t>(1, (A->sendTotal * nvec + 2 * kFusedBlock - 1) / (2 * kFusedBlock)), ctx->numSMs));
   F.dictBegin = A->dictRows > 0 ? A->intBegin : 0;
   F.dictEnd = A->dictRows > 0 ? A->intEnd : 0;
   F.sellBegin = A->genIntBegin;
@@ -1058,7 +1058,13 @@ int applyImpl(const mxg_crs* A, const mxg_mv* x, mxg_mv* y, const Epilogue<T>& e
   X.epoch = nullptr;
   X.halfStride = 0;
   ColTable<T> Y = tableOf<T>(y);
-  if (!halo) return launchRange<T, false>(A, 0, A->nRows, 0, A->nGen, X, Y, nvec, ep);
+  if (!halo) {
+    // MXG_FUSED_SELF=1 (profiling aid): run the single-launch kernel of the multi-rank path on one rank, with empty pack and
+    // boundary roles, so that ncu can look at its interior role
+    const bool fusedSelf = std::getenv("MXG_FUSED_SELF") != nullptr;
+    if (fusedSelf && ctx->nranks == 1 && A->dictRows > 0) return launchFused<T>(A, X, Y, nvec, ep);
+    return launchRange<T, false>(A, 0, A->nRows, 0, A->nGen, X, Y, nvec, ep);
+  }
   if (A->p2p.on && nvec <= A->p2p.capCols) {
     ++A->p2p.hostEpoch;   // one epoch per exchange, on every path, so the device counter and all ranks stay in step
     if (A->p2p.fused && !ctx->profiling) return launchFused<T>(A, X, Y, nvec, ep);

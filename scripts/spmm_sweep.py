@@ -34,11 +34,12 @@ bmap = mx.MxMap(ctx, sim.num_global(field), rg)
 cols = cg[col]
 ENV = {"gather": {"MXG_SPMV_WIN": "0"}, "win3": {"MXG_SPMV_WIN": "1", "MXG_SPMV_ILV": "3"}, "win1": {"MXG_SPMV_WIN": "1", "MXG_SPMV_ILV": "1"},
        "win": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "t"}, "winmv": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "t", "MXG_WIN_MAXVEC": "128"},
+       "fusedself": {"MXG_SPMV_WIN": "0", "MXG_FUSED_SELF": "1"},
        "winp": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "p"}, "winpmv": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "p", "MXG_WIN_MAXVEC": "128"}}
 ref = {}
 out = {}
 for name in args.variants.split(","):
-    for k in ("MXG_SPMV_WIN", "MXG_SPMV_ILV", "MXG_WIN_KERNEL", "MXG_WIN_MAXVEC"):
+    for k in ("MXG_SPMV_WIN", "MXG_SPMV_ILV", "MXG_WIN_KERNEL", "MXG_WIN_MAXVEC", "MXG_FUSED_SELF"):
         os.environ.pop(k, None)
     os.environ.update(ENV[name])
     t = time.time()
@@ -68,4 +69,5 @@ for name in args.variants.split(","):
     out[name] = res
     print(name, json.dumps(res), flush=True)
     del A
+    os.environ.pop("MXG_FUSED_SELF", None)
 print(json.dumps(out))
