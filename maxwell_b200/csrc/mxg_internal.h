@@ -205,6 +205,7 @@ struct mxg_crs {
     unsigned long long* flags = nullptr;    // [nranks] epochs written by the senders, IPC-exported
     unsigned long long* epoch = nullptr;    // local apply counter
     unsigned int* done = nullptr;           // block-completion counter of the pack kernel
+    void* dArgs = nullptr;                  // device copy of the peer tables (P2PArgs) for the single-launch kernel
     unsigned long long* trace = nullptr;    // %globaltimer marks of the fused apply (mxg_crs_trace), NULL = off
     int npeers = 0;
     int peerRank[8];

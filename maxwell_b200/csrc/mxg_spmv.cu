@@ -795,8 +795,10 @@ P2PArgs p2pArgs(const mxg_crs* A) {
 // double buffered by its parity. Reference call: the Epetra_Import inside Epetra_CrsMatrix::Apply (MxCrsMatrix.cpp:347-353).
 constexpr int kFusedBlock = 384;
 struct FusedPlan {
-  int nPack, nDict, nSell;            // blocks per role; boundary blocks follow
-  int64_t dictBegin, dictEnd, sellBegin, sellEnd;
+  int nPack, nDict;                   // blocks per role; boundary blocks follow
+  int64_t dictBegin, dictEnd;         // interior dictionary rows
+  int64_t bnd0Begin, bnd0End, bnd1Begin, bnd1End;   // boundary dictionary rows before / after the interior range
+  int bndBlocks0;
   int ilv;
   unsigned long long epoch;
   unsigned long long* trace;          // optional %globaltimer timeline (mxg_crs_trace): [2 role] = min start, [2 role + 1] = max end
@@ -815,21 +817,25 @@ __device__ __forceinline__ void traceMark(unsigned long long* trace, int role, b
   }
 }
 template <class T, int NV>
-__global__ void __launch_bounds__(kFusedBlock) k_apply_fused(FusedPlan F, P2PArgs P, const int32_t* __restrict__ sendIdx, int64_t sendTotal,
-                                                             unsigned long long* epochDev, unsigned int* done, int capCols, Segments G,
-                                                             DictArgs<T> D, SellArgs<T> S, XSource<T> X, ColTable<T> Y, int nvec,
-                                                             Epilogue<T> ep, WaitArgs W) {
+__global__ void __launch_bounds__(kFusedBlock) k_apply_fused(FusedPlan F, const P2PArgs* __restrict__ P, const int32_t* __restrict__ sendIdx,
+                                                             int64_t sendTotal, unsigned long long* epochDev, unsigned int* done, int capCols,
+                                                             DictArgs<T> D, XSource<T> X, ColTable<T> Y, int nvec, Epilogue<T> ep,
+                                                             const unsigned long long* flags, int* err, long long timeoutTicks) {
+  // The peer tables live in GLOBAL memory (P): indexing a kernel-parameter array with a run-time index makes the compiler
+  // copy it to local memory at kernel entry in EVERY thread; those 160 B of local stores per thread evicted the gather
+  // lines from L1 and cost the interior role 2.3x (ncu: profiles/r02_ncu_fused_self.json).
   int b = blockIdx.x;
   if (b < F.nPack) {
     traceMark(F.trace, 0, false);
     const unsigned long long par = F.epoch & 1ull;
+    const int np = P->n;
     const int64_t total = sendTotal * nvec;
     for (int64_t e = b * int64_t(kFusedBlock) + threadIdx.x; e < total; e += int64_t(F.nPack) * kFusedBlock) {
       const int j = int(e / sendTotal);
       const int64_t i = e - int64_t(j) * sendTotal;
       int k = 0;
-      while (k + 1 < P.n && i >= P.sendOffset[k] + P.sendCount[k]) ++k;
-      T* dst = static_cast<T*>(P.ghost[k]) + (int64_t(par) * capCols + j) * P.remoteGTot[k] + P.remoteStart[k] + (i - P.sendOffset[k]);
+      while (k + 1 < np && i >= P->sendOffset[k] + P->sendCount[k]) ++k;
+      T* dst = static_cast<T*>(P->ghost[k]) + (int64_t(par) * capCols + j) * P->remoteGTot[k] + P->remoteStart[k] + (i - P->sendOffset[k]);
       *dst = X.x.p[j][sendIdx[i]];
     }
     __threadfence_system();
@@ -838,7 +844,7 @@ __global__ void __launch_bounds__(kFusedBlock) k_apply_fused(FusedPlan F, P2PArg
       if (atomicAdd(done, 1u) == unsigned(F.nPack) - 1u) {
         *done = 0u;
         __threadfence_system();
-        for (int k = 0; k < P.n; ++k) *reinterpret_cast<volatile unsigned long long*>(P.flag[k]) = F.epoch;
+        for (int k = 0; k < np; ++k) *reinterpret_cast<volatile unsigned long long*>(P->flag[k]) = F.epoch;
         *epochDev = F.epoch;
         __threadfence_system();
       }
@@ -856,22 +862,14 @@ __global__ void __launch_bounds__(kFusedBlock) k_apply_fused(FusedPlan F, P2PArg
     return;
   }
   b -= F.nDict;
-  if (b < F.nSell) {
-    traceMark(F.trace, 2, false);
-    const int64_t i = F.sellBegin + b * int64_t(kFusedBlock) + threadIdx.x;
-    if (i < F.sellEnd) sellRow<T, false, NV>(i, S, X, Y, nvec, ep);
-    if (F.trace) { __syncthreads(); traceMark(F.trace, 2, true); }
-    return;
-  }
-  b -= F.nSell;
   // boundary rows
   traceMark(F.trace, 3, false);
-  if (threadIdx.x < W.n) {
-    const volatile unsigned long long* f = W.flags + W.senderRank[threadIdx.x];
+  if (int(threadIdx.x) < P->n) {
+    const volatile unsigned long long* f = flags + P->senderRank[threadIdx.x];
     const long long t0 = clock64();
     while (*f < F.epoch) {
-      if (W.timeoutTicks > 0 && clock64() - t0 > W.timeoutTicks) {
-        *W.err = 1;
+      if (timeoutTicks > 0 && clock64() - t0 > timeoutTicks) {
+        *err = 1;
         __threadfence_system();
         asm volatile("trap;");
       }
@@ -882,62 +880,60 @@ __global__ void __launch_bounds__(kFusedBlock) k_apply_fused(FusedPlan F, P2PArg
   __syncthreads();
   traceMark(F.trace, 3, true);
   traceMark(F.trace, 4, false);
-  int seg = 0;
-  while (seg < 3 && b >= G.blockStart[seg + 1]) ++seg;
-  const int64_t idx = G.begin[seg] + int64_t(b - G.blockStart[seg]) * kFusedBlock + threadIdx.x;
-  if (idx < G.end[seg]) {
-    if (seg < 2) dictRow<T, true, NV>(idx, D, X, Y, nvec, ep);
-    else sellRow<T, true, NV>(idx, S, X, Y, nvec, ep);
-  }
+  // two dictionary segments: rows before and after the interior range
+  const bool second = b >= F.bndBlocks0;
+  const int64_t idx = (second ? F.bnd1Begin + int64_t(b - F.bndBlocks0) * kFusedBlock : F.bnd0Begin + int64_t(b) * kFusedBlock) + threadIdx.x;
+  if (idx < (second ? F.bnd1End : F.bnd0End)) dictRow<T, true, NV>(idx, D, X, Y, nvec, ep);
   if (F.trace) { __syncthreads(); traceMark(F.trace, 4, true); }
 }
 
 template <class T>
 int launchFused(const mxg_crs* A, XSource<T> X, const ColTable<T>& Y, int nvec, const Epilogue<T>& ep) {
   mxg_ctx* ctx = A->ctx;
-  const auto& q = A->p2p;
-  const P2PArgs P = p2pArgs<T>(A);
+  auto& q = A->p2p;
+  if (!q.dArgs) {   // device copy of the (static) peer tables
+    const P2PArgs P = p2pArgs<T>(A);
+    MXG_CUDA(cudaMalloc(&q.dArgs, sizeof(P2PArgs)));
+    MXG_CUDA(cudaMemcpyAsync(q.dArgs, &P, sizeof(P2PArgs), cudaMemcpyHostToDevice, ctx->stream));
+    MXG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   FusedPlan F;
-  // enough pack blocks that every thread moves a handful of values: the pack (remote NVLink stores) gates the neighbours'
-  // boundary rows, 8 blocks made it ~100 us long at 2 GPUs (profiles/README_r02.md)
   F.nPack = A->sendTotal == 0 ? 0 : int(std::min<int64_t>(std::max<int64_t>(1, (A->sendTotal * nvec + 2 * kFusedBlock - 1) / (2 * kFusedBlock)), ctx->numSMs));
   F.dictBegin = A->dictRows > 0 ? A->intBegin : 0;
   F.dictEnd = A->dictRows > 0 ? A->intEnd : 0;
-  F.sellBegin = A->genIntBegin;
-  F.sellEnd = A->genIntEnd;
   F.nDict = int((F.dictEnd - F.dictBegin + kFusedBlock - 1) / kFusedBlock);
-  F.nSell = int((F.sellEnd - F.sellBegin + kFusedBlock - 1) / kFusedBlock);
   F.ilv = A->ilv;
   F.epoch = q.hostEpoch;
   F.trace = q.trace;
-  Segments G;
-  const int64_t bb[4] = {0, A->intEnd, 0, A->genIntEnd};
-  const int64_t ee[4] = {A->dictRows > 0 ? A->intBegin : 0, A->dictRows > 0 ? A->nRows : A->intEnd, A->genIntBegin, A->nGen};
-  int blocks = 0;
-  for (int sgm = 0; sgm < 4; ++sgm) {
-    G.begin[sgm] = bb[sgm];
-    G.end[sgm] = ee[sgm] > bb[sgm] ? ee[sgm] : bb[sgm];
-    G.blockStart[sgm] = blocks;
-    blocks += int((G.end[sgm] - G.begin[sgm] + kFusedBlock - 1) / kFusedBlock);
-  }
-  G.blockStart[4] = blocks;
+  F.bnd0Begin = 0;
+  F.bnd0End = A->dictRows > 0 ? A->intBegin : 0;
+  F.bnd1Begin = A->intEnd;
+  F.bnd1End = A->dictRows > 0 ? A->nRows : A->intEnd;
+  F.bndBlocks0 = int((F.bnd0End - F.bnd0Begin + kFusedBlock - 1) / kFusedBlock);
+  const int bndBlocks1 = int((F.bnd1End - F.bnd1Begin + kFusedBlock - 1) / kFusedBlock);
   X.halfStride = int64_t(q.capCols) * X.gTot;
   X.ghost = static_cast<const T*>(q.ghost) + int64_t(F.epoch & 1ull) * X.halfStride;   // this epoch's half of the double buffer
   X.epoch = nullptr;
-  WaitArgs W{};
-  W.n = P.n;
-  W.flags = q.flags;
-  W.epoch = q.epoch;
-  W.err = ctx->dErr;
-  W.timeoutTicks = ctx->haloTimeoutTicks;
-  for (int k = 0; k < P.n; ++k) W.senderRank[k] = P.senderRank[k];
-  const int grid = F.nPack + F.nDict + F.nSell + blocks;
+  // The sliced-ELL rows (cut cells, 0.6 % of the rows) stay out of this kernel: their unrolled index / value arrays cost the
+  // dictionary rows two CTAs per SM. They follow in ONE small launch on the same stream (interior and boundary ranges
+  // together; the flags have been seen by then, so the ghosts are visible).
+  const int grid = F.nPack + F.nDict + F.bndBlocks0 + bndBlocks1;
   const DictArgs<T> D = dictArgs<T>(A);
-  const SellArgs<T> S = sellArgs<T>(A);
-  if (nvec == 1) k_apply_fused<T, 1><<<grid, kFusedBlock, 0, ctx->stream>>>(F, P, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, G, D, S, X, Y, nvec, ep, W);
-  else if (nvec == 2) k_apply_fused<T, 2><<<grid, kFusedBlock, 0, ctx->stream>>>(F, P, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, G, D, S, X, Y, nvec, ep, W);
-  else k_apply_fused<T, 4><<<grid, kFusedBlock, 0, ctx->stream>>>(F, P, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, G, D, S, X, Y, nvec, ep, W);
-  LAUNCH_CHECK(ctx);
+  const P2PArgs* dP = static_cast<const P2PArgs*>(q.dArgs);
+  if (grid > 0) {
+    if (nvec == 1) k_apply_fused<T, 1><<<grid, kFusedBlock, 0, ctx->stream>>>(F, dP, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, D, X, Y, nvec, ep, q.flags, ctx->dErr, ctx->haloTimeoutTicks);
+    else if (nvec == 2) k_apply_fused<T, 2><<<grid, kFusedBlock, 0, ctx->stream>>>(F, dP, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, D, X, Y, nvec, ep, q.flags, ctx->dErr, ctx->haloTimeoutTicks);
+    else k_apply_fused<T, 4><<<grid, kFusedBlock, 0, ctx->stream>>>(F, dP, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, D, X, Y, nvec, ep, q.flags, ctx->dErr, ctx->haloTimeoutTicks);
+    LAUNCH_CHECK(ctx);
+  }
+  if (A->nGen > 0) {
+    const int64_t sblocks = (A->nGen + kBlock - 1) / kBlock;
+    const SellArgs<T> S = sellArgs<T>(A);
+    if (nvec == 1) k_spmm_sell<T, true, 1><<<sblocks, kBlock, 0, ctx->stream>>>(0, A->nGen, S, X, Y, nvec, ep);
+    else if (nvec == 2) k_spmm_sell<T, true, 2><<<sblocks, kBlock, 0, ctx->stream>>>(0, A->nGen, S, X, Y, nvec, ep);
+    else k_spmm_sell<T, true, 4><<<sblocks, kBlock, 0, ctx->stream>>>(0, A->nGen, S, X, Y, nvec, ep);
+    LAUNCH_CHECK(ctx);
+  }
   return MXG_OK;
 }
 
@@ -1657,6 +1653,7 @@ int mxg_crs_destroy(mxg_crs* A) {
   if (A->p2p.epoch) cudaFree(A->p2p.epoch);
   if (A->p2p.done) cudaFree(A->p2p.done);
   if (A->p2p.trace) cudaFree(A->p2p.trace);
+  if (A->p2p.dArgs) cudaFree(A->p2p.dArgs);
   void* ptrs[] = {A->dRowPat, A->dPatOff, A->dPat, A->dGenRow, A->dGenLen, A->dSlicePtr, A->dCol, A->dVal, A->dSendIdx, A->dSendBuf, A->dGhost, A->dInvDiag, A->dWinTiles};
   for (void* p : ptrs)
     if (p) cudaFree(p);
