@@ -344,6 +344,114 @@ __global__ void __launch_bounds__(kWinThreads) k_spmm_win(int64_t rowBegin, int6
   }
 }
 
+// Paired variant: a warp owns 64 consecutive CELLS of one field component (lane l: cells l and l + 32, rows 96 apart), which
+// lie in one z-line more often than not and then share their pattern: one staged slot and one 16-byte entry load serve
+// BOTH rows of the lane. ncu on k_spmm_win (profiles/r02_ncu_win_v2.json): 54 shared wavefronts per 32 rows, 26 of them the x
+// gathers and ~26 the per-row entry loads; this halves the second half and the per-entry address arithmetic.
+template <class T, int ILV>
+__global__ void __launch_bounds__(kWinThreads, 4) k_spmm_win2(int64_t rowBegin, int64_t rowEnd, int64_t tile0, DictArgs<T> D,
+                                                              const WinTile* __restrict__ tiles, XSource<T> X, ColTable<T> Y, int nvec,
+                                                              Epilogue<T> ep) {
+  constexpr int RPT = 2;
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smemRaw);
+  WinTile* Ws = reinterpret_cast<WinTile*>(smemRaw + 64);
+  PatEntry<T>* slots = reinterpret_cast<PatEntry<T>*>(smemRaw + 128);
+  constexpr int kWarps = kWinThreads / 32;
+  T* buf = reinterpret_cast<T*>(smemRaw + 128 + sizeof(PatEntry<T>) * kWarps * RPT * kWinSlot);
+  constexpr int R = kWinThreads * RPT;
+  const int64_t tile = tile0 + blockIdx.x;
+  if (threadIdx.x == 0) {
+    const int4* src = reinterpret_cast<const int4*>(tiles + tile);
+    int4* dst = reinterpret_cast<int4*>(Ws);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = __ldg(src + i);
+    mbarInit(bar, 1);
+    mbarFenceInit();
+    if (Ws->valid) winIssue<T>(*Ws, X.x.p[0], buf, bar);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int rowStride = 32 * ILV;
+  const int64_t row0 = tile * R + (ILV == 3 ? (warp / 3) * (96 * RPT) + 3 * lane + (warp % 3) : warp * (32 * RPT) + lane);
+  int32_t p[RPT], o[RPT], len[RPT];
+  bool uni[RPT];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int64_t row = row0 + i * rowStride;
+    p[i] = -1;
+    if (row >= rowBegin && row < rowEnd) p[i] = D.rowPat[row];
+    o[i] = len[i] = 0;
+    if (p[i] >= 0) { o[i] = __ldg(D.patOff + p[i]); len[i] = __ldg(D.patOff + p[i] + 1) - o[i]; }
+  }
+  int32_t pU[RPT], lenU[RPT];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    pU[i] = __reduce_max_sync(0xffffffffu, p[i]);
+    uni[i] = __all_sync(0xffffffffu, p[i] < 0 || p[i] == pU[i]) && pU[i] >= 0;
+    const int src = __ffs(__ballot_sync(0xffffffffu, p[i] == pU[i])) - 1;
+    const int32_t oU = __shfl_sync(0xffffffffu, o[i], src);
+    lenU[i] = __shfl_sync(0xffffffffu, len[i], src);
+    uni[i] = uni[i] && lenU[i] <= kWinSlot;
+  }
+  const bool pair = uni[0] && uni[1] && pU[0] == pU[1];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    if (pair && i == 1) break;   // slot 0 serves both rows
+    const int src = __ffs(__ballot_sync(0xffffffffu, p[i] == pU[i])) - 1;
+    const int32_t oU = __shfl_sync(0xffffffffu, o[i], src);
+    if (uni[i] && lane < lenU[i]) slots[(warp * RPT + i) * kWinSlot + lane] = ldEntry<T>(D.pat + oU + lane);
+  }
+  __syncthreads();
+  if (!Ws->valid) {   // tile-uniform: gather path
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int64_t row = row0 + i * rowStride;
+      if (row >= rowBegin && row < rowEnd) dictRow<T, false, 1>(row, D, X, Y, nvec, ep);
+    }
+    return;
+  }
+  const WinShift ws{Ws->dLo, Ws->dHi, Ws->shift[0], Ws->shift[1], Ws->shift[2]};
+  const int32_t r0 = int32_t(row0);
+  for (int j = 0; j < nvec; ++j) {
+    mbarWait(bar, j & 1);
+    const T* __restrict__ xs = buf;
+    T* __restrict__ y = Y.p[j];
+    if (pair) {
+      // lanes without a dictionary row (cut cells) must not touch the windows: their offsets may fall outside
+      const bool v0 = len[0] > 0, v1 = len[1] > 0;
+      const PatEntry<T>* __restrict__ ent = slots + (warp * RPT) * kWinSlot;
+      T a0 = zeroOf<T>(), a1 = zeroOf<T>();
+      const T* xa = xs + (v0 ? r0 : (v1 ? r0 + rowStride : 0));
+      const T* xb = xs + (v1 ? r0 + rowStride : (v0 ? r0 : 0));
+      const int32_t n = lenU[0];
+      if (v0 || v1) {
+        for (int32_t q = 0; q < n; ++q) {
+          const PatEntry<T> e = ldEntry<T>(ent + q);
+          const int32_t off = e.d + (e.d < ws.dLo ? ws.s0 : (e.d > ws.dHi ? ws.s2 : ws.s1));
+          const T xv0 = xa[off], xv1 = xb[off];
+          accum(a0, entryVal(e), xv0);
+          accum(a1, entryVal(e), xv1);
+        }
+      }
+      if (v0) storeY(y, row0, a0, ep);
+      if (v1) storeY(y, row0 + rowStride, a1, ep);
+    } else {
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        if (len[i] == 0) continue;
+        const int32_t r = r0 + i * rowStride;
+        const T acc = uni[i] ? winRowDot<T>(slots + (warp * RPT + i) * kWinSlot, len[i], r, xs, ws)
+                             : winRowDot<T>(D.pat + o[i], len[i], r, xs, ws);
+        storeY(y, row0 + i * rowStride, acc, ep);
+      }
+    }
+    if (j + 1 < nvec) {
+      __syncthreads();   // everyone is done with the windows of vector j
+      if (threadIdx.x == 0) winIssue<T>(*Ws, X.x.p[j + 1], buf, bar);
+    }
+  }
+}
+
 template <class T, bool GHOST, int NV>
 __global__ void __launch_bounds__(kBlock) k_spmm_sell(int64_t genBegin, int64_t genEnd, SellArgs<T> S,
                                                       XSource<T> X, ColTable<T> Y, int nvec, Epilogue<T> ep) {
@@ -647,6 +755,22 @@ int launchWin(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, const XSource<
   const size_t smem = winSmemHeader<T>() + size_t(A->winBufElems) * sizeof(T);
   const DictArgs<T> D = dictArgs<T>(A);
   const WinTile* wt = static_cast<const WinTile*>(A->dWinTiles);
+  if constexpr (RPT == 2) {
+    if (A->winKernel == 2) {   // paired rows
+      static bool attr2[2] = {false, false};
+      if (A->winIlv == 3) {
+        auto kern = k_spmm_win2<T, 3>;
+        if (!attr2[0]) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWinSmemMax))); attr2[0] = true; }
+        kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, D, wt, X, Y, nvec, ep);
+      } else {
+        auto kern = k_spmm_win2<T, 1>;
+        if (!attr2[1]) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWinSmemMax))); attr2[1] = true; }
+        kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, D, wt, X, Y, nvec, ep);
+      }
+      LAUNCH_CHECK(ctx);
+      return MXG_OK;
+    }
+  }
   static bool attrSet[2] = {false, false};
   if (A->winIlv == 3) {
     auto kern = k_spmm_win<T, 3, RPT>;
@@ -910,7 +1034,10 @@ int launchFused(const mxg_crs* A, XSource<T> X, const ColTable<T>& Y, int nvec, 
   F.bnd1Begin = A->intEnd;
   F.bnd1End = A->dictRows > 0 ? A->nRows : A->intEnd;
   F.bndBlocks0 = int((F.bnd0End - F.bnd0Begin + kFusedBlock - 1) / kFusedBlock);
-  const int bndBlocks1 = int((F.bnd1End - F.bnd1Begin + kFusedBlock - 1) / kFusedBlock);
+  int bndBlocks1 = int((F.bnd1End - F.bnd1Begin + kFusedBlock - 1) / kFusedBlock);
+  // the boundary blocks are also what WAITS for the neighbours' flags before the sliced-ELL launch below may read ghosts:
+  // keep one of them even when no dictionary row needs a ghost (sliced-ELL-only layouts)
+  if (A->sendTotal > 0 && F.bndBlocks0 + bndBlocks1 == 0) bndBlocks1 = 1;
   X.halfStride = int64_t(q.capCols) * X.gTot;
   X.ghost = static_cast<const T*>(q.ghost) + int64_t(F.epoch & 1ull) * X.halfStride;   // this epoch's half of the double buffer
   X.epoch = nullptr;
@@ -1499,7 +1626,7 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
         A->winValid = valid;
         A->winBufElems = maxTotal;
         A->winMaxVec = 1;
-        if (const char* wk = std::getenv("MXG_WIN_KERNEL")) A->winKernel = std::strcmp(wk, "p") == 0 ? 1 : 0;
+        if (const char* wk = std::getenv("MXG_WIN_KERNEL")) A->winKernel = std::strcmp(wk, "p") == 0 ? 1 : (std::strcmp(wk, "2") == 0 ? 2 : 0);
         if (const char* mv = std::getenv("MXG_WIN_MAXVEC")) A->winMaxVec = std::atoi(mv);
         // thread -> row assignment: component triples (GID = comp + 3 cell) share patterns at distance 3, scalar fields at 1
         int64_t same1 = 0, same3 = 0;

@@ -35,6 +35,7 @@ cols = cg[col]
 ENV = {"gather": {"MXG_SPMV_WIN": "0"}, "win3": {"MXG_SPMV_WIN": "1", "MXG_SPMV_ILV": "3"}, "win1": {"MXG_SPMV_WIN": "1", "MXG_SPMV_ILV": "1"},
        "win": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "t"}, "winmv": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "t", "MXG_WIN_MAXVEC": "128"},
        "fusedself": {"MXG_SPMV_WIN": "0", "MXG_FUSED_SELF": "1"},
+       "win2": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "2"}, "win2mv": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "2", "MXG_WIN_MAXVEC": "128"},
        "winp": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "p"}, "winpmv": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "p", "MXG_WIN_MAXVEC": "128"}}
 ref = {}
 out = {}
