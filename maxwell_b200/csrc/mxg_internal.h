@@ -182,7 +182,6 @@ struct mxg_crs {
   void* dWinTiles = nullptr;           // WinTile[winTiles]
   int winR = 0;                        // rows per tile (0 = windowed path off)
   int winIlv = 1;                      // thread -> row assignment inside a tile (1 or 3)
-  int winKernel = 0;                   // 0: one tile per CTA (entries in shared slots), 1: persistent pipelined CTAs (entries in registers)
   int winMaxVec = 1;                   // widest block the windowed kernel takes (wider blocks: gather kernels)
   int64_t winTiles = 0, winValid = 0;  // tiles / tiles served from shared memory
   int64_t winBufElems = 0;             // largest window set of any tile (scalars)

@@ -344,114 +344,6 @@ __global__ void __launch_bounds__(kWinThreads) k_spmm_win(int64_t rowBegin, int6
   }
 }
 
-// Paired variant: a warp owns 64 consecutive CELLS of one field component (lane l: cells l and l + 32, rows 96 apart), which
-// lie in one z-line more often than not and then share their pattern: one staged slot and one 16-byte entry load serve
-// BOTH rows of the lane. ncu on k_spmm_win (profiles/r02_ncu_win_v2.json): 54 shared wavefronts per 32 rows, 26 of them the x
-// gathers and ~26 the per-row entry loads; this halves the second half and the per-entry address arithmetic.
-template <class T, int ILV>
-__global__ void __launch_bounds__(kWinThreads, 4) k_spmm_win2(int64_t rowBegin, int64_t rowEnd, int64_t tile0, DictArgs<T> D,
-                                                              const WinTile* __restrict__ tiles, XSource<T> X, ColTable<T> Y, int nvec,
-                                                              Epilogue<T> ep) {
-  constexpr int RPT = 2;
-  extern __shared__ __align__(128) unsigned char smemRaw[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smemRaw);
-  WinTile* Ws = reinterpret_cast<WinTile*>(smemRaw + 64);
-  PatEntry<T>* slots = reinterpret_cast<PatEntry<T>*>(smemRaw + 128);
-  constexpr int kWarps = kWinThreads / 32;
-  T* buf = reinterpret_cast<T*>(smemRaw + 128 + sizeof(PatEntry<T>) * kWarps * RPT * kWinSlot);
-  constexpr int R = kWinThreads * RPT;
-  const int64_t tile = tile0 + blockIdx.x;
-  if (threadIdx.x == 0) {
-    const int4* src = reinterpret_cast<const int4*>(tiles + tile);
-    int4* dst = reinterpret_cast<int4*>(Ws);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i] = __ldg(src + i);
-    mbarInit(bar, 1);
-    mbarFenceInit();
-    if (Ws->valid) winIssue<T>(*Ws, X.x.p[0], buf, bar);
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int rowStride = 32 * ILV;
-  const int64_t row0 = tile * R + (ILV == 3 ? (warp / 3) * (96 * RPT) + 3 * lane + (warp % 3) : warp * (32 * RPT) + lane);
-  int32_t p[RPT], o[RPT], len[RPT];
-  bool uni[RPT];
-#pragma unroll
-  for (int i = 0; i < RPT; ++i) {
-    const int64_t row = row0 + i * rowStride;
-    p[i] = -1;
-    if (row >= rowBegin && row < rowEnd) p[i] = D.rowPat[row];
-    o[i] = len[i] = 0;
-    if (p[i] >= 0) { o[i] = __ldg(D.patOff + p[i]); len[i] = __ldg(D.patOff + p[i] + 1) - o[i]; }
-  }
-  int32_t pU[RPT], lenU[RPT];
-#pragma unroll
-  for (int i = 0; i < RPT; ++i) {
-    pU[i] = __reduce_max_sync(0xffffffffu, p[i]);
-    uni[i] = __all_sync(0xffffffffu, p[i] < 0 || p[i] == pU[i]) && pU[i] >= 0;
-    const int src = __ffs(__ballot_sync(0xffffffffu, p[i] == pU[i])) - 1;
-    const int32_t oU = __shfl_sync(0xffffffffu, o[i], src);
-    lenU[i] = __shfl_sync(0xffffffffu, len[i], src);
-    uni[i] = uni[i] && lenU[i] <= kWinSlot;
-  }
-  const bool pair = uni[0] && uni[1] && pU[0] == pU[1];
-#pragma unroll
-  for (int i = 0; i < RPT; ++i) {
-    if (pair && i == 1) break;   // slot 0 serves both rows
-    const int src = __ffs(__ballot_sync(0xffffffffu, p[i] == pU[i])) - 1;
-    const int32_t oU = __shfl_sync(0xffffffffu, o[i], src);
-    if (uni[i] && lane < lenU[i]) slots[(warp * RPT + i) * kWinSlot + lane] = ldEntry<T>(D.pat + oU + lane);
-  }
-  __syncthreads();
-  if (!Ws->valid) {   // tile-uniform: gather path
-#pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-      const int64_t row = row0 + i * rowStride;
-      if (row >= rowBegin && row < rowEnd) dictRow<T, false, 1>(row, D, X, Y, nvec, ep);
-    }
-    return;
-  }
-  const WinShift ws{Ws->dLo, Ws->dHi, Ws->shift[0], Ws->shift[1], Ws->shift[2]};
-  const int32_t r0 = int32_t(row0);
-  for (int j = 0; j < nvec; ++j) {
-    mbarWait(bar, j & 1);
-    const T* __restrict__ xs = buf;
-    T* __restrict__ y = Y.p[j];
-    if (pair) {
-      // lanes without a dictionary row (cut cells) must not touch the windows: their offsets may fall outside
-      const bool v0 = len[0] > 0, v1 = len[1] > 0;
-      const PatEntry<T>* __restrict__ ent = slots + (warp * RPT) * kWinSlot;
-      T a0 = zeroOf<T>(), a1 = zeroOf<T>();
-      const T* xa = xs + (v0 ? r0 : (v1 ? r0 + rowStride : 0));
-      const T* xb = xs + (v1 ? r0 + rowStride : (v0 ? r0 : 0));
-      const int32_t n = lenU[0];
-      if (v0 || v1) {
-        for (int32_t q = 0; q < n; ++q) {
-          const PatEntry<T> e = ldEntry<T>(ent + q);
-          const int32_t off = e.d + (e.d < ws.dLo ? ws.s0 : (e.d > ws.dHi ? ws.s2 : ws.s1));
-          const T xv0 = xa[off], xv1 = xb[off];
-          accum(a0, entryVal(e), xv0);
-          accum(a1, entryVal(e), xv1);
-        }
-      }
-      if (v0) storeY(y, row0, a0, ep);
-      if (v1) storeY(y, row0 + rowStride, a1, ep);
-    } else {
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        if (len[i] == 0) continue;
-        const int32_t r = r0 + i * rowStride;
-        const T acc = uni[i] ? winRowDot<T>(slots + (warp * RPT + i) * kWinSlot, len[i], r, xs, ws)
-                             : winRowDot<T>(D.pat + o[i], len[i], r, xs, ws);
-        storeY(y, row0 + i * rowStride, acc, ep);
-      }
-    }
-    if (j + 1 < nvec) {
-      __syncthreads();   // everyone is done with the windows of vector j
-      if (threadIdx.x == 0) winIssue<T>(*Ws, X.x.p[j + 1], buf, bar);
-    }
-  }
-}
-
 template <class T, bool GHOST, int NV>
 __global__ void __launch_bounds__(kBlock) k_spmm_sell(int64_t genBegin, int64_t genEnd, SellArgs<T> S,
                                                       XSource<T> X, ColTable<T> Y, int nvec, Epilogue<T> ep) {
@@ -552,187 +444,6 @@ int launchSegments(const mxg_crs* A, const int64_t b[4], const int64_t e[4], con
 }
 
 
-// ---- persistent, pipelined variant of the windowed kernel --------------------------------------------------------------------
-// Two lessons from the versions above (ncu, profiles/README_r02.md): (i) re-reading the pattern entries from shared memory for
-// every row costs as many load wavefronts as the x gathers themselves -- keep them in REGISTERS (RegPattern): a warp owns
-// 32 * RPT consecutive cells of one field component, which share a pattern inside a z-line, so one set of <= 14
-// (value, shared-offset) pairs serves RPT rows per lane and every vector of a block; (ii) that costs ~80 registers, i.e. two
-// 384-thread CTAs per SM, which is too little to hide a TMA round trip per tile -- so the CTA is PERSISTENT and prefetches:
-// a ring of STAGES window buffers, thread 0 issues the bulk copies of work item m + STAGES as soon as item m's buffer is
-// released. A work item is (tile, vector): block applies stream the columns through the same ring.
-constexpr int kWinRegs = 14;   // pattern entries kept in registers (longer rows take the per-lane path)
-struct WinShift2 {
-  int32_t dLo, dHi, s0, s1, s2;
-  __device__ __forceinline__ int32_t of(int32_t d) const { return d + (d < dLo ? s0 : (d > dHi ? s2 : s1)); }
-};
-template <class T>
-struct RegPattern {
-  T v[kWinRegs];
-  int32_t off[kWinRegs];
-  int32_t len;
-  __device__ __forceinline__ void load(const PatEntry<T>* __restrict__ pat, int32_t n, const WinShift2& w) {
-    len = n;
-#pragma unroll
-    for (int q = 0; q < kWinRegs; ++q) {
-      v[q] = zeroOf<T>();
-      off[q] = 0;
-      if (q < n) {
-        const PatEntry<T> e = ldEntry<T>(pat + q);
-        v[q] = entryVal(e);
-        off[q] = w.of(e.d);
-      }
-    }
-  }
-  // NR rows of this thread, r0 + i * stride; ascending column order, separately rounded multiply and add
-  template <int NR>
-  __device__ __forceinline__ void dot(const T* __restrict__ xs, int32_t r0, int32_t stride, T (&acc)[NR]) const {
-#pragma unroll
-    for (int i = 0; i < NR; ++i) acc[i] = zeroOf<T>();
-#pragma unroll
-    for (int q = 0; q < kWinRegs; ++q)
-      if (q < len) {
-        const T* px = xs + r0 + off[q];
-#pragma unroll
-        for (int i = 0; i < NR; ++i) accum(acc[i], v[q], px[i * stride]);
-      }
-  }
-};
-template <class T>
-__device__ __forceinline__ T winRowDot2(const PatEntry<T>* __restrict__ ent, int32_t len, int32_t r, const T* __restrict__ xs, const WinShift2& w) {
-  T acc = zeroOf<T>();
-  for (int32_t q = 0; q < len; ++q) {
-    const PatEntry<T> e0 = ldEntry<T>(ent + q);
-    accum(acc, entryVal(e0), xs[r + w.of(e0.d)]);
-  }
-  return acc;
-}
-
-template <class T, int ILV, int RPT, int STAGES>
-__global__ void __launch_bounds__(kWinThreads, 2) k_spmm_winp(int64_t rowBegin, int64_t rowEnd, int64_t tile0, int64_t nTiles, DictArgs<T> D,
-                                                              const WinTile* __restrict__ tiles, int bufElems, XSource<T> X, ColTable<T> Y,
-                                                              int nvec, Epilogue<T> ep) {
-  extern __shared__ __align__(128) unsigned char smemRaw[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smemRaw);          // STAGES barriers
-  T* buf = reinterpret_cast<T*>(smemRaw + 128);
-  constexpr int R = kWinThreads * RPT;
-  // this CTA's tiles: blockIdx.x, blockIdx.x + gridDim.x, ...; work item m = (tile m / nvec, vector m % nvec)
-  const int64_t nMine = (nTiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  const int64_t nItems = nMine * nvec;
-  auto issue = [&](int64_t m) {   // thread 0 only
-    const int64_t tile = tile0 + blockIdx.x + (m / nvec) * gridDim.x;
-    const int s = int(m % STAGES);
-    const WinTile* W = tiles + tile;
-    if (__ldg(&W->valid)) {
-      uint32_t bytes = 0;
-      int32_t lo[3], ln[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { lo[k] = __ldg(&W->segLo[k]); ln[k] = __ldg(&W->segLen[k]); bytes += uint32_t(ln[k]) * uint32_t(sizeof(T)); }
-      mbarExpectTx(&bar[s], bytes);
-      const T* xcol = X.x.p[int(m % nvec)];
-      int off = 0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (ln[k] > 0) bulkLoad(buf + int64_t(s) * bufElems + off, xcol + lo[k], uint32_t(ln[k]) * uint32_t(sizeof(T)), &bar[s]);
-        off += ln[k];
-      }
-    } else {
-      mbarExpectTx(&bar[s], 0);   // gather-path tile: nothing to stage, complete the phase
-    }
-  };
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbarInit(&bar[s], 1);
-    mbarFenceInit();
-    for (int64_t m = 0; m < STAGES && m < nItems; ++m) issue(m);
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int rowStride = 32 * ILV;
-  const int tOff = ILV == 3 ? (warp / 3) * (96 * RPT) + 3 * lane + (warp % 3) : warp * (32 * RPT) + lane;
-  RegPattern<T> P;
-  int32_t p[RPT], o[RPT], len[RPT];
-  bool uniAll = false, valid = false;
-  WinShift2 ws{0, 0, 0, 0, 0};
-  int64_t row0 = 0;
-  for (int64_t m = 0; m < nItems; ++m) {
-    const int j = int(m % nvec);
-    const int s = int(m % STAGES);
-    if (j == 0) {   // new tile: row patterns
-      const int64_t tile = tile0 + blockIdx.x + (m / nvec) * gridDim.x;
-      const WinTile* W = tiles + tile;
-      valid = __ldg(&W->valid) != 0;
-      ws = WinShift2{__ldg(&W->dLo), __ldg(&W->dHi), __ldg(&W->shift[0]), __ldg(&W->shift[1]), __ldg(&W->shift[2])};
-      row0 = tile * R + tOff;
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        const int64_t row = row0 + i * rowStride;
-        p[i] = -1;
-        if (row >= rowBegin && row < rowEnd) p[i] = D.rowPat[row];
-        o[i] = len[i] = 0;
-        if (p[i] >= 0) { o[i] = __ldg(D.patOff + p[i]); len[i] = __ldg(D.patOff + p[i] + 1) - o[i]; }
-      }
-      const int32_t p0 = __shfl_sync(0xffffffffu, p[0], 0);
-      bool mine = p0 >= 0;
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) mine = mine && p[i] == p0;
-      uniAll = valid && __all_sync(0xffffffffu, mine) && len[0] <= kWinRegs;
-      if (uniAll) P.load(D.pat + o[0], len[0], ws);
-    }
-    mbarWait(&bar[s], uint32_t((m / STAGES) & 1));
-    if (!valid) {
-      if (j == 0) {
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-          const int64_t row = row0 + i * rowStride;
-          if (row >= rowBegin && row < rowEnd) dictRow<T, false, 1>(row, D, X, Y, nvec, ep);   // all vectors at once
-        }
-      }
-    } else {
-      const T* __restrict__ xs = buf + int64_t(s) * bufElems;
-      T* __restrict__ y = Y.p[j];
-      if (uniAll) {
-        T acc[RPT];
-        P.template dot<RPT>(xs, int32_t(row0), rowStride, acc);
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) storeY(y, row0 + i * rowStride, acc[i], ep);
-      } else {
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-          const int32_t pi0 = __shfl_sync(0xffffffffu, p[i], 0);
-          const bool uni = __all_sync(0xffffffffu, p[i] == pi0 && pi0 >= 0) && len[i] <= kWinRegs;
-          if (uni) {     // a z-line ends elsewhere in this warp's cells, this row slot is still uniform
-            P.load(D.pat + o[i], len[i], ws);
-            T acc[1];
-            P.template dot<1>(xs, int32_t(row0 + i * rowStride), 0, acc);
-            storeY(y, row0 + i * rowStride, acc[0], ep);
-          } else if (len[i] > 0) {
-            storeY(y, row0 + i * rowStride, winRowDot2<T>(D.pat + o[i], len[i], int32_t(row0 + i * rowStride), xs, ws), ep);
-          }
-        }
-      }
-    }
-    __syncthreads();                                       // stage s is free again
-    if (threadIdx.x == 0 && m + STAGES < nItems) issue(m + STAGES);
-  }
-}
-
-template <class T, int ILV, int RPT>
-int launchWinP(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, const XSource<T>& X, const ColTable<T>& Y, int nvec,
-               const Epilogue<T>& ep, cudaStream_t st) {
-  constexpr int STAGES = 2;
-  const int R = A->winR;
-  const int64_t tile0 = rowBegin / R, tiles = (rowEnd + R - 1) / R - tile0;
-  const size_t smem = 128 + size_t(STAGES) * size_t(A->winBufElems) * sizeof(T);
-  auto kern = k_spmm_winp<T, ILV, RPT, STAGES>;
-  static bool attrSet = false;
-  if (!attrSet) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attrSet = true; }
-  const int grid = int(std::min<int64_t>(tiles, int64_t(A->ctx->numSMs) * (2 * smem + 2048 <= 227 * 1024 ? 2 : 1)));
-  kern<<<grid, kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, tiles, dictArgs<T>(A), static_cast<const WinTile*>(A->dWinTiles),
-                                         int(A->winBufElems), X, Y, nvec, ep);
-  LAUNCH_CHECK(A->ctx);
-  return MXG_OK;
-}
-
 // rows per thread of the windowed kernel (tile = kWinThreads * RPT rows)
 template <class T> struct WinCfg;
 template <> struct WinCfg<double> { static constexpr int RPT = 2; };
@@ -747,30 +458,11 @@ int launchWin(const mxg_crs* A, int64_t rowBegin, int64_t rowEnd, const XSource<
               const Epilogue<T>& ep, cudaStream_t st) {
   mxg_ctx* ctx = A->ctx;
   constexpr int RPT = WinCfg<T>::RPT;
-  if (A->winKernel == 1 && 128 + 2 * size_t(A->winBufElems) * sizeof(T) <= 110 * 1024) {
-    return A->winIlv == 3 ? launchWinP<T, 3, RPT>(A, rowBegin, rowEnd, X, Y, nvec, ep, st) : launchWinP<T, 1, RPT>(A, rowBegin, rowEnd, X, Y, nvec, ep, st);
-  }
   const int R = A->winR;
   const int64_t tile0 = rowBegin / R, tiles = (rowEnd + R - 1) / R - tile0;
   const size_t smem = winSmemHeader<T>() + size_t(A->winBufElems) * sizeof(T);
   const DictArgs<T> D = dictArgs<T>(A);
   const WinTile* wt = static_cast<const WinTile*>(A->dWinTiles);
-  if constexpr (RPT == 2) {
-    if (A->winKernel == 2) {   // paired rows
-      static bool attr2[2] = {false, false};
-      if (A->winIlv == 3) {
-        auto kern = k_spmm_win2<T, 3>;
-        if (!attr2[0]) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWinSmemMax))); attr2[0] = true; }
-        kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, D, wt, X, Y, nvec, ep);
-      } else {
-        auto kern = k_spmm_win2<T, 1>;
-        if (!attr2[1]) { MXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWinSmemMax))); attr2[1] = true; }
-        kern<<<unsigned(tiles), kWinThreads, smem, st>>>(rowBegin, rowEnd, tile0, D, wt, X, Y, nvec, ep);
-      }
-      LAUNCH_CHECK(ctx);
-      return MXG_OK;
-    }
-  }
   static bool attrSet[2] = {false, false};
   if (A->winIlv == 3) {
     auto kern = k_spmm_win<T, 3, RPT>;
@@ -1626,7 +1318,6 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
         A->winValid = valid;
         A->winBufElems = maxTotal;
         A->winMaxVec = 1;
-        if (const char* wk = std::getenv("MXG_WIN_KERNEL")) A->winKernel = std::strcmp(wk, "p") == 0 ? 1 : (std::strcmp(wk, "2") == 0 ? 2 : 0);
         if (const char* mv = std::getenv("MXG_WIN_MAXVEC")) A->winMaxVec = std::atoi(mv);
         // thread -> row assignment: component triples (GID = comp + 3 cell) share patterns at distance 3, scalar fields at 1
         int64_t same1 = 0, same3 = 0;

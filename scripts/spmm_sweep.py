@@ -17,7 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=256)
 ap.add_argument("--op", default="curlCurl")
 ap.add_argument("--workload", default="pillbox")
-ap.add_argument("--variants", default="gather,win3,win1")
+ap.add_argument("--variants", default="gather,win,winmv")
 ap.add_argument("--nvecs", default="1,4,10")
 ap.add_argument("--reps", type=int, default=50)
 args = ap.parse_args()
@@ -32,15 +32,12 @@ ctx = mx.Context(0)
 field = "psifield" if args.op == "scaLapl" else "bfield"
 bmap = mx.MxMap(ctx, sim.num_global(field), rg)
 cols = cg[col]
-ENV = {"gather": {"MXG_SPMV_WIN": "0"}, "win3": {"MXG_SPMV_WIN": "1", "MXG_SPMV_ILV": "3"}, "win1": {"MXG_SPMV_WIN": "1", "MXG_SPMV_ILV": "1"},
-       "win": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "t"}, "winmv": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "t", "MXG_WIN_MAXVEC": "128"},
-       "fusedself": {"MXG_SPMV_WIN": "0", "MXG_FUSED_SELF": "1"},
-       "win2": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "2"}, "win2mv": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "2", "MXG_WIN_MAXVEC": "128"},
-       "winp": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "p"}, "winpmv": {"MXG_SPMV_WIN": "1", "MXG_WIN_KERNEL": "p", "MXG_WIN_MAXVEC": "128"}}
+ENV = {"gather": {"MXG_SPMV_WIN": "0"}, "win": {"MXG_SPMV_WIN": "1"}, "winmv": {"MXG_SPMV_WIN": "1", "MXG_WIN_MAXVEC": "128"},
+       "win_ilv1": {"MXG_SPMV_WIN": "1", "MXG_SPMV_ILV": "1"}, "fusedself": {"MXG_SPMV_WIN": "0", "MXG_FUSED_SELF": "1"}}
 ref = {}
 out = {}
 for name in args.variants.split(","):
-    for k in ("MXG_SPMV_WIN", "MXG_SPMV_ILV", "MXG_WIN_KERNEL", "MXG_WIN_MAXVEC", "MXG_FUSED_SELF"):
+    for k in ("MXG_SPMV_WIN", "MXG_SPMV_ILV", "MXG_WIN_MAXVEC", "MXG_FUSED_SELF"):
         os.environ.pop(k, None)
     os.environ.update(ENV[name])
     t = time.time()

@@ -203,15 +203,13 @@ def test_literal_reference_operator_r13(mx, ctx, orc):
     assert not np.array_equal(got_l, got_d)
 
 
-@pytest.mark.parametrize("kernel", ["t", "2", "p"])
 @pytest.mark.parametrize("name,size", [("curlCurl", 48), ("vecLapl", 40), ("scaLapl", 40)])
-def test_windowed_kernel_equals_gather_kernel(mx, ctx, orc, name, size, kernel, monkeypatch):
+def test_windowed_kernel_equals_gather_kernel(mx, ctx, orc, name, size, monkeypatch):
     """The windowed dictionary kernel (x windows staged in shared memory by 1-D TMA, mxg_spmm_win.cuh) against the gather
     kernels (MXG_SPMV_WIN=0) and the oracle, on grids large enough for many tiles; block applies and the fused epilogue."""
     sim = orc.pillbox(size)
     monkeypatch.setenv("MXG_SPMV_WIN", "1")
     monkeypatch.setenv("MXG_WIN_MAXVEC", "128")          # default: windowed kernel for single vectors only
-    monkeypatch.setenv("MXG_WIN_KERNEL", kernel)         # t: one tile per CTA; 2: same with paired rows; p: persistent pipelined CTAs, patterns in registers
     Aw, op, rmap, cmap = gpu_matrix(mx, ctx, sim, name)
     monkeypatch.setenv("MXG_SPMV_WIN", "0")
     Ag, _, _, _ = gpu_matrix(mx, ctx, sim, name)
