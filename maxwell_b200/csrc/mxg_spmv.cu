@@ -194,6 +194,22 @@ __device__ __forceinline__ void sellRow(int64_t i, const SellArgs<T>& S, const X
   }
 }
 
+// Sliced-ELL row without the unrolled index / value arrays of sellRow (those cost the single-launch kernel 16 registers and
+// one CTA per SM); used for the few cut-cell rows inside k_apply_fused only. Same arithmetic order, bit-identical.
+template <class T, bool GHOST>
+__device__ __forceinline__ void sellRowSimple(int64_t i, const SellArgs<T>& S, const XSource<T>& X, const ColTable<T>& Y, int nvec,
+                                              const Epilogue<T>& ep) {
+  const int64_t row = S.genRow[i];
+  if (row < 0) return;
+  const int len = S.genLen[i];
+  const int64_t base = S.slicePtr[i >> 5] + (i & 31);
+  for (int j = 0; j < nvec; ++j) {
+    T acc = zeroOf<T>();
+    for (int k = 0; k < len; ++k) accum(acc, S.val[base + int64_t(k) * 32], loadX<T, GHOST>(X, j, S.col[base + int64_t(k) * 32]));
+    storeY(Y.p[j], row, acc, ep);
+  }
+}
+
 template <class T, bool GHOST, int NV>
 __global__ void __launch_bounds__(kBlock) k_spmm_dict(int64_t rowBegin, int64_t rowEnd, DictArgs<T> D,
                                                       XSource<T> X, ColTable<T> Y, int nvec, Epilogue<T> ep) {
@@ -614,7 +630,8 @@ struct FusedPlan {
   int nPack, nDict;                   // blocks per role; boundary blocks follow
   int64_t dictBegin, dictEnd;         // interior dictionary rows
   int64_t bnd0Begin, bnd0End, bnd1Begin, bnd1End;   // boundary dictionary rows before / after the interior range
-  int bndBlocks0;
+  int bndBlocks0, bndBlocks1;
+  int64_t nGen;                       // sliced-ELL rows (compacted index space)
   int ilv;
   unsigned long long epoch;
   unsigned long long* trace;          // optional %globaltimer timeline (mxg_crs_trace): [2 role] = min start, [2 role + 1] = max end
@@ -633,10 +650,11 @@ __device__ __forceinline__ void traceMark(unsigned long long* trace, int role, b
   }
 }
 template <class T, int NV>
-__global__ void __launch_bounds__(kFusedBlock) k_apply_fused(FusedPlan F, const P2PArgs* __restrict__ P, const int32_t* __restrict__ sendIdx,
+__global__ void __launch_bounds__(kFusedBlock, (NV == 1 && sizeof(T) == 8) ? 5 : (NV <= 2 ? 4 : 3)) k_apply_fused(FusedPlan F, const P2PArgs* __restrict__ P, const int32_t* __restrict__ sendIdx,
                                                              int64_t sendTotal, unsigned long long* epochDev, unsigned int* done, int capCols,
-                                                             DictArgs<T> D, XSource<T> X, ColTable<T> Y, int nvec, Epilogue<T> ep,
-                                                             const unsigned long long* flags, int* err, long long timeoutTicks) {
+                                                             DictArgs<T> D, SellArgs<T> S, XSource<T> X, ColTable<T> Y, int nvec,
+                                                             Epilogue<T> ep, const unsigned long long* flags, int* err,
+                                                             long long timeoutTicks) {
   // The peer tables live in GLOBAL memory (P): indexing a kernel-parameter array with a run-time index makes the compiler
   // copy it to local memory at kernel entry in EVERY thread; those 160 B of local stores per thread evicted the gather
   // lines from L1 and cost the interior role 2.3x (ncu: profiles/r02_ncu_fused_self.json).
@@ -696,10 +714,16 @@ __global__ void __launch_bounds__(kFusedBlock) k_apply_fused(FusedPlan F, const 
   __syncthreads();
   traceMark(F.trace, 3, true);
   traceMark(F.trace, 4, false);
-  // two dictionary segments: rows before and after the interior range
-  const bool second = b >= F.bndBlocks0;
-  const int64_t idx = (second ? F.bnd1Begin + int64_t(b - F.bndBlocks0) * kFusedBlock : F.bnd0Begin + int64_t(b) * kFusedBlock) + threadIdx.x;
-  if (idx < (second ? F.bnd1End : F.bnd0End)) dictRow<T, true, NV>(idx, D, X, Y, nvec, ep);
+  // two dictionary segments (rows before and after the interior range), then ALL sliced-ELL rows (cut cells, 0.6 % of the
+  // rows; those among them that need no ghost simply find none)
+  if (b < F.bndBlocks0 + F.bndBlocks1) {
+    const bool second = b >= F.bndBlocks0;
+    const int64_t idx = (second ? F.bnd1Begin + int64_t(b - F.bndBlocks0) * kFusedBlock : F.bnd0Begin + int64_t(b) * kFusedBlock) + threadIdx.x;
+    if (idx < (second ? F.bnd1End : F.bnd0End)) dictRow<T, true, NV>(idx, D, X, Y, nvec, ep);
+  } else {
+    const int64_t i = int64_t(b - F.bndBlocks0 - F.bndBlocks1) * kFusedBlock + threadIdx.x;
+    if (i < F.nGen) sellRowSimple<T, true>(i, S, X, Y, nvec, ep);
+  }
   if (F.trace) { __syncthreads(); traceMark(F.trace, 4, true); }
 }
 
@@ -726,31 +750,22 @@ int launchFused(const mxg_crs* A, XSource<T> X, const ColTable<T>& Y, int nvec, 
   F.bnd1Begin = A->intEnd;
   F.bnd1End = A->dictRows > 0 ? A->nRows : A->intEnd;
   F.bndBlocks0 = int((F.bnd0End - F.bnd0Begin + kFusedBlock - 1) / kFusedBlock);
-  int bndBlocks1 = int((F.bnd1End - F.bnd1Begin + kFusedBlock - 1) / kFusedBlock);
-  // the boundary blocks are also what WAITS for the neighbours' flags before the sliced-ELL launch below may read ghosts:
-  // keep one of them even when no dictionary row needs a ghost (sliced-ELL-only layouts)
-  if (A->sendTotal > 0 && F.bndBlocks0 + bndBlocks1 == 0) bndBlocks1 = 1;
+  F.bndBlocks1 = int((F.bnd1End - F.bnd1Begin + kFusedBlock - 1) / kFusedBlock);
+  F.nGen = A->nGen;
+  // the blocks after the interior rows are also what WAITS for the neighbours' flags: keep one even when nothing reads a ghost
+  int sellBlocks = int((A->nGen + kFusedBlock - 1) / kFusedBlock);
+  if (A->sendTotal > 0 && F.bndBlocks0 + F.bndBlocks1 + sellBlocks == 0) F.bndBlocks1 = 1;
   X.halfStride = int64_t(q.capCols) * X.gTot;
   X.ghost = static_cast<const T*>(q.ghost) + int64_t(F.epoch & 1ull) * X.halfStride;   // this epoch's half of the double buffer
   X.epoch = nullptr;
-  // The sliced-ELL rows (cut cells, 0.6 % of the rows) stay out of this kernel: their unrolled index / value arrays cost the
-  // dictionary rows two CTAs per SM. They follow in ONE small launch on the same stream (interior and boundary ranges
-  // together; the flags have been seen by then, so the ghosts are visible).
-  const int grid = F.nPack + F.nDict + F.bndBlocks0 + bndBlocks1;
+  const int grid = F.nPack + F.nDict + F.bndBlocks0 + F.bndBlocks1 + sellBlocks;
   const DictArgs<T> D = dictArgs<T>(A);
+  const SellArgs<T> S = sellArgs<T>(A);
   const P2PArgs* dP = static_cast<const P2PArgs*>(q.dArgs);
   if (grid > 0) {
-    if (nvec == 1) k_apply_fused<T, 1><<<grid, kFusedBlock, 0, ctx->stream>>>(F, dP, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, D, X, Y, nvec, ep, q.flags, ctx->dErr, ctx->haloTimeoutTicks);
-    else if (nvec == 2) k_apply_fused<T, 2><<<grid, kFusedBlock, 0, ctx->stream>>>(F, dP, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, D, X, Y, nvec, ep, q.flags, ctx->dErr, ctx->haloTimeoutTicks);
-    else k_apply_fused<T, 4><<<grid, kFusedBlock, 0, ctx->stream>>>(F, dP, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, D, X, Y, nvec, ep, q.flags, ctx->dErr, ctx->haloTimeoutTicks);
-    LAUNCH_CHECK(ctx);
-  }
-  if (A->nGen > 0) {
-    const int64_t sblocks = (A->nGen + kBlock - 1) / kBlock;
-    const SellArgs<T> S = sellArgs<T>(A);
-    if (nvec == 1) k_spmm_sell<T, true, 1><<<sblocks, kBlock, 0, ctx->stream>>>(0, A->nGen, S, X, Y, nvec, ep);
-    else if (nvec == 2) k_spmm_sell<T, true, 2><<<sblocks, kBlock, 0, ctx->stream>>>(0, A->nGen, S, X, Y, nvec, ep);
-    else k_spmm_sell<T, true, 4><<<sblocks, kBlock, 0, ctx->stream>>>(0, A->nGen, S, X, Y, nvec, ep);
+    if (nvec == 1) k_apply_fused<T, 1><<<grid, kFusedBlock, 0, ctx->stream>>>(F, dP, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, D, S, X, Y, nvec, ep, q.flags, ctx->dErr, ctx->haloTimeoutTicks);
+    else if (nvec == 2) k_apply_fused<T, 2><<<grid, kFusedBlock, 0, ctx->stream>>>(F, dP, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, D, S, X, Y, nvec, ep, q.flags, ctx->dErr, ctx->haloTimeoutTicks);
+    else k_apply_fused<T, 4><<<grid, kFusedBlock, 0, ctx->stream>>>(F, dP, A->dSendIdx, A->sendTotal, q.epoch, q.done, q.capCols, D, S, X, Y, nvec, ep, q.flags, ctx->dErr, ctx->haloTimeoutTicks);
     LAUNCH_CHECK(ctx);
   }
   return MXG_OK;
