@@ -47,6 +47,19 @@ template <> struct ScalarTraits<MxComplex> {
   static MxComplex zero() { return MxComplex(0.0, 0.0); }
 };
 
+#ifdef MX_HAVE_ANASAZI
+}  // namespace mx
+// With Trilinos present the shims derive from the real interfaces: MxAnasaziMV IS an Anasazi::MultiVec and
+// can be handed to BlockKrylovSchurSolMgr / BlockDavidsonSolMgr exactly as in src/MxSolver.cpp:62-94. (Trilinos is absent from
+// this build container, so this branch is not compiled here.)
+#include "AnasaziMultiVec.hpp"
+#include "AnasaziOperator.hpp"
+#include "Teuchos_SerialDenseMatrix.hpp"
+namespace mx {
+template <class Ordinal, class Scalar> using SerialDenseMatrix = Teuchos::SerialDenseMatrix<Ordinal, Scalar>;
+template <class Scalar> using MultiVec = Anasazi::MultiVec<Scalar>;
+template <class Scalar> using Operator = Anasazi::Operator<Scalar>;
+#else
 // Look-alike of Teuchos::SerialDenseMatrix<int, Scalar> (column-major host matrix): the subset
 // the reference touches -- numRows/numCols/values/stride/operator() (MxAnasaziMV.cpp:12-14,45-52).
 template <class Ordinal, class Scalar>
@@ -102,6 +115,8 @@ class Operator {
   virtual ~Operator() {}
   virtual void Apply(const MultiVec<Scalar>& x, MultiVec<Scalar>& y) const = 0;
 };
+
+#endif  // MX_HAVE_ANASAZI
 
 // A constraint the eigensolver keeps its search space in (MxSolverT::setConstraint): the divergence-free subspace.
 template <class S>

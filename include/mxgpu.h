@@ -175,6 +175,8 @@ int mxg_crs_create(mxg_map* row_map, mxg_map* domain_map, const int64_t* rowptr,
  * mxg_crs_create reads the default from the environment variable MXG_SPMV_LAYOUT=dict|sell. */
 int mxg_crs_create_opts(mxg_map* row_map, mxg_map* domain_map, const int64_t* rowptr, const int64_t* col_gids,
                         const double* vals, int is_complex, int layout, mxg_crs** out);
+/* On several ranks an operator with a peer-memory halo owns buffers its neighbours have mapped (CUDA IPC): destroy it on every
+ * rank at the same point of the program, after a barrier / synchronisation of all ranks (no rank may still be applying it). */
 int mxg_crs_destroy(mxg_crs* A);
 /* apply (MxCrsMatrix.cpp:347-353): y = A x; x over the domain map, y over the row map.
  * On several ranks the ghost entries of x are exchanged with NCCL send/recv, overlapped

@@ -74,23 +74,8 @@ MvStorage::~MvStorage() {
 
 using namespace mxg;
 
-extern "C" {
-
-const char* mxg_last_error(void) { return g_err; }
-int mxg_version(void) { return 100; }
-
-int mxg_ctx_create(int device, mxg_ctx** out) {
-  MXG_REQUIRE(out != nullptr, "mxg_ctx_create: out is NULL");
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev == 0) {
-    setError("mxg_ctx_create: no CUDA device available (%s); libmxgpu has no CPU fallback",
-             e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-    return MXG_ERR_CUDA;
-  }
-  MXG_REQUIRE(device >= 0 && device < ndev, "mxg_ctx_create: device %d out of range (0..%d)", device, ndev - 1);
-  MXG_CUDA(cudaSetDevice(device));
-  mxg_ctx* ctx = new mxg_ctx;
+namespace {
+static int ctxInit(mxg_ctx* ctx, int device) {
   ctx->device = device;
   ctx->graphsOff = std::getenv("MXG_NO_GRAPH") != nullptr;   // eager enqueues instead of graph replay
   MXG_CUDA(cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device));
@@ -116,8 +101,33 @@ int mxg_ctx_create(int device, mxg_ctx** out) {
   MXG_CUDA(cudaMalloc(&ctx->dDense, 64 * 1024));
   int rc = ensureScratch(ctx, 1u << 20);
   if (rc) return rc;
-  rc = ensurePinned(ctx, 1u << 20);
-  if (rc) return rc;
+  return ensurePinned(ctx, 1u << 20);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mxg_last_error(void) { return g_err; }
+int mxg_version(void) { return 100; }
+
+int mxg_ctx_create(int device, mxg_ctx** out) {
+  MXG_REQUIRE(out != nullptr, "mxg_ctx_create: out is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    setError("mxg_ctx_create: no CUDA device available (%s); libmxgpu has no CPU fallback",
+             e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return MXG_ERR_CUDA;
+  }
+  MXG_REQUIRE(device >= 0 && device < ndev, "mxg_ctx_create: device %d out of range (0..%d)", device, ndev - 1);
+  MXG_CUDA(cudaSetDevice(device));
+  mxg_ctx* ctx = new mxg_ctx;
+  const int rc = ctxInit(ctx, device);
+  if (rc) {   // one cleanup path: whatever was created so far is released
+    mxg_ctx_destroy(ctx);
+    return rc;
+  }
   *out = ctx;
   return MXG_OK;
 }
@@ -125,21 +135,21 @@ int mxg_ctx_create(int device, mxg_ctx** out) {
 int mxg_ctx_destroy(mxg_ctx* ctx) {
   if (!ctx) return MXG_OK;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  cudaStreamSynchronize(ctx->commStream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->commStream) cudaStreamSynchronize(ctx->commStream);
   if (ctx->comm) ncclCommDestroy(ctx->comm);
   if (ctx->dScratch) cudaFree(ctx->dScratch);
   if (ctx->dDense) cudaFree(ctx->dDense);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
   if (ctx->hErr) cudaFreeHost(ctx->hErr);
-  cudaEventDestroy(ctx->evA);
-  cudaEventDestroy(ctx->evB);
+  if (ctx->evA) cudaEventDestroy(ctx->evA);
+  if (ctx->evB) cudaEventDestroy(ctx->evB);
   for (auto& e : ctx->timer)
     if (e) cudaEventDestroy(e);
   for (auto& e : ctx->prof)
     if (e) cudaEventDestroy(e);
-  cudaStreamDestroy(ctx->stream);
-  cudaStreamDestroy(ctx->commStream);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
   delete ctx;
   return MXG_OK;
 }
@@ -245,7 +255,13 @@ int mxg_map_create_ordered(mxg_ctx* ctx, int64_t n_global, const int64_t* my_gid
   int rc = mxg_map_create(ctx, n_global, my_gids, n_local, out);
   if (rc || ncomp == 1 || n_local == 0) return rc;
   mxg_map* m = *out;
-  m->perm = mxg::componentMajorOrder(my_gids, n_local, ncomp);
+  try {
+    m->perm = mxg::componentMajorOrder(my_gids, n_local, ncomp);
+  } catch (const std::exception& e) {   // nothing may unwind through the C boundary
+    mxg_map_destroy(m);
+    *out = nullptr;
+    MXG_REQUIRE(false, "mxg_map_create_ordered: %s", e.what());
+  }
   bool identity = true;
   for (int64_t i = 0; i < n_local && identity; ++i) identity = m->perm[size_t(i)] == int32_t(i);
   if (identity) { m->perm.clear(); return MXG_OK; }

@@ -153,8 +153,8 @@ int vcycle(mxg_gmg* g, int l, mxg_mv* x, const mxg_mv* b, bool zeroStart) {
   const int nc = x->ncols;
   mxg_mv *r = nullptr, *bc = nullptr, *xc = nullptr;
   if ((rc = viewCols(g->v[l], nc, &r))) return rc;
-  if ((rc = viewCols(g->b[l + 1], nc, &bc))) return rc;
-  if ((rc = viewCols(g->x[l + 1], nc, &xc))) return rc;
+  if ((rc = viewCols(g->b[l + 1], nc, &bc))) { mxg_mv_destroy(r); return rc; }
+  if ((rc = viewCols(g->x[l + 1], nc, &xc))) { mxg_mv_destroy(r); mxg_mv_destroy(bc); return rc; }
   const double one[2] = {1, 0}, mone[2] = {-1, 0};
   // r = b - A x  (fused SpMM epilogue)
   rc = mxg_mv_assign(r, b);
@@ -186,7 +186,7 @@ int estimateLambdaMax(mxg_gmg* g, int l, int iters, double* out) {
   mxg_mv *u = nullptr, *t = nullptr;
   int rc = mxg_mv_create(A->rowMap, 1, g->isComplex, &u);
   if (rc) return rc;
-  if ((rc = mxg_mv_create(A->rowMap, 1, g->isComplex, &t))) return rc;
+  if ((rc = mxg_mv_create(A->rowMap, 1, g->isComplex, &t))) { mxg_mv_destroy(u); return rc; }
   mxg_mv_random(u, 0x5eedull + l);
   double lam = 1.0, nrm = 0.0;
   for (int it = 0; it < iters && !rc; ++it) {

@@ -850,7 +850,7 @@ int mxg_mv_to_grid(const mxg_mv* mv, int col, int64_t gid_lo, int64_t gid_hi, do
   dErr = reinterpret_cast<int*>(dOut + size_t(len) * parts);
   cudaError_t e = cudaMemsetAsync(dOut, 0, size_t(len) * parts * sizeof(double) + sizeof(int), ctx->stream);
   if (e == cudaSuccess && n > 0) {
-    const int blocks = int(std::min<int64_t>((n + 255) / 256, 148 * 8));
+    const int blocks = int(std::min<int64_t>((n + 255) / 256, int64_t(ctx->numSMs) * 8));
     k_scatter_grid<<<blocks, 256, 0, ctx->stream>>>(static_cast<const double*>(mv->col[col]), parts, mv->map->dGids, n, gid_lo, gid_hi,
                                                     dOut, dOut + len, dErr);
     ++ctx->launches;

@@ -1205,7 +1205,11 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
     std::vector<int64_t> rp2;
     std::vector<int32_t> ext2;
     std::vector<T> val2;
-    mxg::permuteCsr(rp, ext, val, rowPerm, colInv, nLoc, rp2, ext2, val2);
+    try {
+      mxg::permuteCsr(rp, ext, val, rowPerm, colInv, nLoc, rp2, ext2, val2);
+    } catch (const std::exception& e) {   // nothing may unwind through the C boundary
+      MXG_REQUIRE(false, "mxg_crs_create: %s", e.what());
+    }
     rp.swap(rp2);
     ext.swap(ext2);
     val.swap(val2);
