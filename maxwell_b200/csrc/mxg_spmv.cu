@@ -631,7 +631,8 @@ struct FusedPlan {
   int64_t dictBegin, dictEnd;         // interior dictionary rows
   int64_t bnd0Begin, bnd0End, bnd1Begin, bnd1End;   // boundary dictionary rows before / after the interior range
   int bndBlocks0, bndBlocks1;
-  int64_t nGen;                       // sliced-ELL rows (compacted index space)
+  int nSellInt;                       // blocks of interior sliced-ELL rows (they run before the dictionary rows)
+  int64_t sellIntBegin, sellIntEnd, nGen;   // sliced-ELL rows (compacted index space): interior range / all
   int ilv;
   unsigned long long epoch;
   unsigned long long* trace;          // optional %globaltimer timeline (mxg_crs_trace): [2 role] = min start, [2 role + 1] = max end
@@ -687,6 +688,14 @@ __global__ void __launch_bounds__(kFusedBlock, (NV == 1 && sizeof(T) == 8) ? 5 :
     return;
   }
   b -= F.nPack;
+  if (b < F.nSellInt) {   // interior cut-cell rows: latency-bound (one dependent gather per entry), so they start early
+    traceMark(F.trace, 2, false);
+    const int64_t i = F.sellIntBegin + b * int64_t(kFusedBlock) + threadIdx.x;
+    if (i < F.sellIntEnd) sellRowSimple<T, false>(i, S, X, Y, nvec, ep);
+    if (F.trace) { __syncthreads(); traceMark(F.trace, 2, true); }
+    return;
+  }
+  b -= F.nSellInt;
   if (b < F.nDict) {
     traceMark(F.trace, 1, false);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -714,14 +723,14 @@ __global__ void __launch_bounds__(kFusedBlock, (NV == 1 && sizeof(T) == 8) ? 5 :
   __syncthreads();
   traceMark(F.trace, 3, true);
   traceMark(F.trace, 4, false);
-  // two dictionary segments (rows before and after the interior range), then ALL sliced-ELL rows (cut cells, 0.6 % of the
-  // rows; those among them that need no ghost simply find none)
+  // two dictionary segments (rows before and after the interior range), then the sliced-ELL rows that read ghosts
   if (b < F.bndBlocks0 + F.bndBlocks1) {
     const bool second = b >= F.bndBlocks0;
     const int64_t idx = (second ? F.bnd1Begin + int64_t(b - F.bndBlocks0) * kFusedBlock : F.bnd0Begin + int64_t(b) * kFusedBlock) + threadIdx.x;
     if (idx < (second ? F.bnd1End : F.bnd0End)) dictRow<T, true, NV>(idx, D, X, Y, nvec, ep);
-  } else {
-    const int64_t i = int64_t(b - F.bndBlocks0 - F.bndBlocks1) * kFusedBlock + threadIdx.x;
+  } else {   // boundary cut-cell rows: the compacted ranges before and after the interior one
+    int64_t i = int64_t(b - F.bndBlocks0 - F.bndBlocks1) * kFusedBlock + threadIdx.x;
+    if (i >= F.sellIntBegin) i += F.sellIntEnd - F.sellIntBegin;
     if (i < F.nGen) sellRowSimple<T, true>(i, S, X, Y, nvec, ep);
   }
   if (F.trace) { __syncthreads(); traceMark(F.trace, 4, true); }
@@ -752,13 +761,16 @@ int launchFused(const mxg_crs* A, XSource<T> X, const ColTable<T>& Y, int nvec, 
   F.bndBlocks0 = int((F.bnd0End - F.bnd0Begin + kFusedBlock - 1) / kFusedBlock);
   F.bndBlocks1 = int((F.bnd1End - F.bnd1Begin + kFusedBlock - 1) / kFusedBlock);
   F.nGen = A->nGen;
+  F.sellIntBegin = A->genIntBegin;
+  F.sellIntEnd = A->genIntEnd;
+  F.nSellInt = int((F.sellIntEnd - F.sellIntBegin + kFusedBlock - 1) / kFusedBlock);
   // the blocks after the interior rows are also what WAITS for the neighbours' flags: keep one even when nothing reads a ghost
-  int sellBlocks = int((A->nGen + kFusedBlock - 1) / kFusedBlock);
+  int sellBlocks = int((A->nGen - (F.sellIntEnd - F.sellIntBegin) + kFusedBlock - 1) / kFusedBlock);
   if (A->sendTotal > 0 && F.bndBlocks0 + F.bndBlocks1 + sellBlocks == 0) F.bndBlocks1 = 1;
   X.halfStride = int64_t(q.capCols) * X.gTot;
   X.ghost = static_cast<const T*>(q.ghost) + int64_t(F.epoch & 1ull) * X.halfStride;   // this epoch's half of the double buffer
   X.epoch = nullptr;
-  const int grid = F.nPack + F.nDict + F.bndBlocks0 + F.bndBlocks1 + sellBlocks;
+  const int grid = F.nPack + F.nSellInt + F.nDict + F.bndBlocks0 + F.bndBlocks1 + sellBlocks;
   const DictArgs<T> D = dictArgs<T>(A);
   const SellArgs<T> S = sellArgs<T>(A);
   const P2PArgs* dP = static_cast<const P2PArgs*>(q.dArgs);
