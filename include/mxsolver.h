@@ -28,7 +28,7 @@ typedef struct mxs_projection {
   mxg_gmg* sca_prec;      /* multigrid on the scalar hierarchy, or NULL = Jacobi */
   double tol_init;        /* relative accuracy of the inner CG: initial block (0 = 1e-6) */
   double tol_w;           /* ... preconditioned residuals, every iteration (0 = 0.1) */
-  double tol_x;           /* ... re-projection of the iterate (0 = 1e-3) */
+  double tol_x;           /* ... re-projection of the iterate (0 = 1e-2) */
   double reproject_ratio; /* re-project X when |D M x|/|M x| > ratio * max(relative residual, tol) (0 = 0.05) */
   int max_iters;          /* inner CG iteration cap (0 = 500) */
   int max_iters_w;        /* cap for the per-iteration projections of the preconditioned residuals (0 = none) */
