@@ -1,0 +1,259 @@
+// Operator assembly on the device (include/mxasm.h): cut-cell fractions of a CSG shape, DOF maps,
+// the Yee operator generators and the CRS products / sums that chain them into curlCurl, gradDiv, vecLapl and scaLapl,
+// one thread per cell or per operator row. The arithmetic lives in mxg_yee.h / mxg_shape.h (host/device code, replayed on
+// the CPU by the tests); this file supplies the CUDA executor: kernels, a three-pass prefix scan, memory.
+//
+// This translation unit is compiled with -fmad=false: the reference's host code rounds a*b+c twice, and the generated
+// matrices have to carry the very same doubles for the SpMV parity gate to hold downstream.
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+#include "mxasm.h"
+#include "mxg_internal.h"
+#include "mxg_asm_impl.h"
+#include "mxg_shape.h"
+
+namespace {
+
+constexpr int kAsmBlock = 256;
+constexpr int kScanChunk = 2048;    // items per block of the scan passes (8 per thread)
+
+template <class F>
+__global__ void __launch_bounds__(kAsmBlock) k_asm_rows(int64_t n, F f) {
+  for (int64_t i = int64_t(blockIdx.x) * kAsmBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kAsmBlock) f(i);
+}
+
+// pass 1: per-chunk totals
+__global__ void __launch_bounds__(kAsmBlock) k_scan_sums(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ sums) {
+  __shared__ int64_t sh[kAsmBlock];
+  const int64_t base = int64_t(blockIdx.x) * kScanChunk;
+  int64_t s = 0;
+  for (int k = 0; k < kScanChunk / kAsmBlock; ++k) {
+    const int64_t i = base + int64_t(k) * kAsmBlock + threadIdx.x;
+    if (i < n) s += in[i];
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = kAsmBlock / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sums[blockIdx.x] = sh[0];
+}
+// pass 2: exclusive scan of the chunk totals in one block (a running carry over tiles of kAsmBlock totals)
+__global__ void __launch_bounds__(kAsmBlock) k_scan_chunks(int64_t* __restrict__ sums, int64_t numChunks, int64_t* __restrict__ total) {
+  __shared__ int64_t sh[kAsmBlock];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t tile = 0; tile < numChunks; tile += kAsmBlock) {
+    const int64_t i = tile + threadIdx.x;
+    const int64_t v = i < numChunks ? sums[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < kAsmBlock; o <<= 1) {       // inclusive Hillis-Steele
+      const int64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < numChunks) sums[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == kAsmBlock - 1) carry += sh[kAsmBlock - 1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+// pass 3: exclusive scan inside every chunk, offset by the chunk's start; thread t owns 8 consecutive items
+__global__ void __launch_bounds__(kAsmBlock) k_scan_write(const int32_t* __restrict__ in, int64_t n, const int64_t* __restrict__ sums,
+                                                          const int64_t* __restrict__ total, int64_t* __restrict__ out) {
+  __shared__ int64_t sh[kAsmBlock];
+  constexpr int per = kScanChunk / kAsmBlock;
+  const int64_t first = int64_t(blockIdx.x) * kScanChunk + int64_t(threadIdx.x) * per;
+  int32_t v[per];
+  int64_t s = 0;
+  for (int k = 0; k < per; ++k) {
+    v[k] = first + k < n ? in[first + k] : 0;
+    s += v[k];
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < kAsmBlock; o <<= 1) {
+    const int64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  int64_t run = sums[blockIdx.x] + sh[threadIdx.x] - s;
+  for (int k = 0; k < per; ++k) {
+    if (first + k < n) out[first + k] = run;
+    run += v[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *total;
+}
+
+__global__ void __launch_bounds__(kAsmBlock) k_asm_max(const int32_t* __restrict__ in, int64_t n, int* __restrict__ out) {
+  int m = 0;
+  for (int64_t i = int64_t(blockIdx.x) * kAsmBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kAsmBlock) m = max(m, in[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+[[noreturn]] void fail(const char* what, cudaError_t e) {
+  throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+struct DeviceExec {
+  mxg_ctx* ctx;
+  explicit DeviceExec(mxg_ctx* c) : ctx(c) {
+    if (!c) throw std::runtime_error("operator assembly needs a context (mxg_ctx_create)");
+    cudaSetDevice(c->device);
+  }
+  template <class T>
+  T* alloc(int64_t n) {
+    void* p = nullptr;
+    const cudaError_t e = cudaMalloc(&p, size_t(n > 0 ? n : 1) * sizeof(T));
+    if (e != cudaSuccess) fail("device allocation of the operator assembly", e);
+    return static_cast<T*>(p);
+  }
+  void free(void* p) { if (p) cudaFree(p); }
+  void check(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) fail(what, e);
+  }
+  template <class F>
+  void forEach(int64_t n, const F& f) {
+    static_assert(sizeof(F) <= 3072, "row functor too large for a kernel parameter block");
+    if (n <= 0) return;
+    const int64_t blocks = std::min<int64_t>((n + kAsmBlock - 1) / kAsmBlock, int64_t(1) << 30);
+    k_asm_rows<F><<<unsigned(blocks), kAsmBlock, 0, ctx->stream>>>(n, f);
+    ctx->launches++;
+    check("assembly kernel launch");
+  }
+  int64_t scan(const int32_t* in, int64_t* out, int64_t n) {
+    const int64_t chunks = std::max<int64_t>((n + kScanChunk - 1) / kScanChunk, 1);
+    int64_t* sums = alloc<int64_t>(chunks + 1);
+    k_scan_sums<<<unsigned(chunks), kAsmBlock, 0, ctx->stream>>>(in, n, sums);
+    k_scan_chunks<<<1, kAsmBlock, 0, ctx->stream>>>(sums, chunks, sums + chunks);
+    k_scan_write<<<unsigned(chunks), kAsmBlock, 0, ctx->stream>>>(in, n, sums, sums + chunks, out);
+    ctx->launches += 3;
+    check("prefix scan launch");
+    int64_t total = 0;
+    toHost(&total, sums + chunks, sizeof(int64_t));
+    free(sums);
+    return total;
+  }
+  int maxOf(const int32_t* in, int64_t n) {
+    int* d = alloc<int>(1);
+    cudaMemsetAsync(d, 0, sizeof(int), ctx->stream);
+    const int64_t blocks = std::min<int64_t>((n + kAsmBlock - 1) / kAsmBlock, 4096);
+    if (n > 0) {
+      k_asm_max<<<unsigned(blocks), kAsmBlock, 0, ctx->stream>>>(in, n, d);
+      ctx->launches++;
+    }
+    check("row maximum launch");
+    int m = 0;
+    toHost(&m, d, sizeof(int));
+    free(d);
+    return m;
+  }
+  void toHost(void* dst, const void* src, size_t bytes) {
+    if (!bytes) return;
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) fail("device -> host copy of the operator assembly", e);
+  }
+  void toExec(void* dst, const void* src, size_t bytes) {
+    if (!bytes) return;
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // the source may be a stack temporary
+    if (e != cudaSuccess) fail("host -> device copy of the operator assembly", e);
+  }
+  void sync() {
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) fail("operator assembly", e);
+  }
+};
+
+}  // namespace
+
+#define MXA_FN(name) mxg_##name
+#define MXA_EXEC DeviceExec
+#define MXA_CTX mxg_ctx
+#define MXA_SIM_T mxg_sim
+#define MXA_DCSR_T mxg_dcsr
+#define MXA_SHAPE_T mxg_shape
+#define MXA_NEW_EXEC(ctx) (new DeviceExec(ctx))
+#define MXA_FAIL(code, msg)        \
+  do {                             \
+    mxg::setError("%s", (msg));    \
+    return (code);                 \
+  } while (0)
+
+#include "mxg_asm_api.inc"
+
+extern "C" {
+
+// MxCrsMatrix::fillComplete for an operator assembled on the device (MxCrsMatrix.cpp:325-342): the rows this rank's
+// row map owns become a device operator (pattern dictionary / sliced ELL, halo plan) without the host ever generating
+// them. The rows pass through the host once, for the layout builder of mxg_crs_create.
+int mxg_crs_create_from_dcsr(mxg_map* row_map, mxg_map* domain_map, const mxg_dcsr* a, int layout, mxg_crs** out) {
+  const CsrHandle* A = reinterpret_cast<const CsrHandle*>(a);
+  MXG_REQUIRE(row_map && domain_map && A && out, "mxg_crs_create_from_dcsr: NULL argument");
+  const int rf = A->rowField(), cf = A->colField();
+  MXG_REQUIRE(rf >= 0 && cf >= 0, "mxg_crs_create_from_dcsr: the matrix does not know which fields its rows and columns live on");
+  try {
+    mxa::Assembler<DeviceExec>& as = *A->sim->as;
+    MXG_REQUIRE(domain_map->nGlobal == as.numGlobal(cf) && row_map->nGlobal == as.numGlobal(rf),
+                "mxg_crs_create_from_dcsr: maps do not span the simulation's GID space");
+    std::vector<int64_t> rowG(static_cast<size_t>(as.mapSize(rf)), 0), colG(static_cast<size_t>(as.mapSize(cf)), 0);
+    as.copyMap(rf, rowG.data());
+    as.copyMap(cf, colG.data());
+    // the rank's rows: one contiguous run of the field map (x-slabs)
+    int64_t r0 = 0, r1 = 0;
+    if (row_map->nLocal > 0) {
+      r0 = int64_t(std::lower_bound(rowG.begin(), rowG.end(), row_map->gids.front()) - rowG.begin());
+      r1 = r0 + row_map->nLocal;
+      MXG_REQUIRE(r1 <= int64_t(rowG.size()) && std::memcmp(rowG.data() + r0, row_map->gids.data(), size_t(row_map->nLocal) * sizeof(int64_t)) == 0,
+                  "mxg_crs_create_from_dcsr: the row map is not a contiguous run of the simulation's %s map",
+                  rf == mxy::FIELD_B ? "B" : (rf == mxy::FIELD_E ? "E" : "psi"));
+    }
+    const int64_t n = r1 - r0;
+    std::vector<int64_t> rowptr(static_cast<size_t>(n) + 1, 0);
+    int rc = mxg_dcsr_download(a, r0, r1, rowptr.data(), nullptr, nullptr);
+    if (rc) return rc;
+    const int64_t cnt = rowptr[size_t(n)];
+    std::vector<int32_t> col(static_cast<size_t>(std::max<int64_t>(cnt, 1)), 0);
+    std::vector<double> val(static_cast<size_t>(std::max<int64_t>(cnt, 1)) * (A->isComplex ? 2 : 1), 0.0);
+    rc = mxg_dcsr_download(a, r0, r1, rowptr.data(), col.data(), val.data());
+    if (rc) return rc;
+    std::vector<int64_t> gcol(static_cast<size_t>(std::max<int64_t>(cnt, 1)), 0);
+    for (int64_t q = 0; q < cnt; ++q) gcol[size_t(q)] = colG[size_t(col[size_t(q)])];
+    std::vector<int32_t>().swap(col);
+    return mxg_crs_create_opts(row_map, domain_map, rowptr.data(), gcol.data(), val.data(), A->isComplex, layout, out);
+  } catch (const std::exception& e) {
+    MXG_REQUIRE(false, "mxg_crs_create_from_dcsr: %s", e.what());
+  }
+}
+
+// The DOF map of a field as an mxg_map of this context: the rows [begin, end) of the field's map (an x-slab when the
+// caller cuts at plane boundaries), or the whole map with begin = 0, end = -1.
+int mxg_sim_make_map(mxg_sim* sim, const char* field, int64_t begin, int64_t end, mxg_map** out) {
+  SimHandle* h = reinterpret_cast<SimHandle*>(sim);
+  const int k = fieldIndex(field);
+  MXG_REQUIRE(h && k >= 0 && out, "mxg_sim_make_map: bad argument");
+  MXG_REQUIRE(h->as->isSetUp(), "mxg_sim_make_map: call mxg_sim_setup first");
+  try {
+    const int64_t n = h->as->mapSize(k);
+    if (end < 0) end = n;
+    MXG_REQUIRE(begin >= 0 && begin <= end && end <= n, "mxg_sim_make_map: range outside the map");
+    std::vector<int64_t> g(static_cast<size_t>(n), 0);
+    h->as->copyMap(k, g.data());
+    return mxg_map_create(h->ctx, h->as->numGlobal(k), g.data() + begin, end - begin, out);
+  } catch (const std::exception& e) {
+    MXG_REQUIRE(false, "mxg_sim_make_map: %s", e.what());
+  }
+}
+
+}  // extern "C"

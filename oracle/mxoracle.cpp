@@ -159,6 +159,20 @@ int mxo_sim_map_fracs(void* s, const char* field, double* out) {
   });
 }
 
+// fractions of a named shape representation ("pec", "diel0", ...) on the guarded block: (N+3)^3 cells x components.
+// Returns the value count (0 when the field has no such representation); `out` may be NULL to query it.
+int64_t mxo_sim_rep_copy(void* s, const char* field, const char* rep, double* out) {
+  int64_t n = -1;
+  guard([&] {
+    const Field* f = fieldOf(static_cast<Sim*>(s), field);
+    auto it = f->reps.find(rep);
+    if (it == f->reps.end()) { n = 0; return; }
+    n = int64_t(it->second.size());
+    if (out) std::memcpy(out, it->second.data(), it->second.size() * sizeof(double));
+  });
+  return n;
+}
+
 // ---- operators --------------------------------------------------------------------------
 void* mxo_build_op(void* s, const char* name, int is_complex) {
   Mat* m = new Mat;

@@ -63,6 +63,7 @@ def lib():
             "mxo_sim_map_size": (i64, [vp, cp]),
             "mxo_sim_map_copy": (C.c_int, [vp, cp, vp]),
             "mxo_sim_map_num_global": (i64, [vp, cp]),
+            "mxo_sim_rep_copy": (i64, [vp, cp, cp, vp]),
             "mxo_sim_map_fracs": (C.c_int, [vp, cp, vp]),
             "mxo_build_op": (vp, [vp, cp, C.c_int]),
             "mxo_mat_kform": (vp, [vp]),
@@ -315,6 +316,17 @@ class Sim:
         n = lib().mxo_sim_map_size(self.h, field.encode())
         out = np.empty(n, dtype=np.float64)
         _check(lib().mxo_sim_map_fracs(self.h, field.encode(), out.ctypes.data))
+        return out
+
+    def full_fracs(self, field, rep="pec"):
+        """Fractions of a shape representation on the guarded block ((N+3)^3 cells x components); None if absent."""
+        n = lib().mxo_sim_rep_copy(self.h, field.encode(), rep.encode(), None)
+        if n < 0:
+            raise RuntimeError(lib().mxo_last_error().decode())
+        if n == 0:
+            return None
+        out = np.empty(n, dtype=np.float64)
+        lib().mxo_sim_rep_copy(self.h, field.encode(), rep.encode(), out.ctypes.data)
         return out
 
     def op(self, name, is_complex=None):

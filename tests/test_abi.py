@@ -8,8 +8,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "mxgpu.h")).read()
+def declared_symbols(header="mxgpu.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(mxg_[a-z0-9_]+)\s*\(", text)))
 
@@ -25,6 +25,23 @@ def test_header_symbols_are_exported(mx):
     for s in syms:
         assert hasattr(L, s)
     assert L.mxg_version() >= 100
+
+
+def test_assembly_header_symbols_are_exported(mx):
+    """include/mxasm.h (operator assembly) is served by the same library."""
+    syms = declared_symbols("mxasm.h")
+    assert len(syms) >= 38
+    out = subprocess.check_output(["nm", "-D", "--defined-only", mx.library_path()], text=True)
+    exported = set(re.findall(r" T (mxg_[a-z0-9_]+)", out))
+    missing = [s for s in syms if s not in exported]
+    assert not missing, "declared in mxasm.h but not exported: %s" % missing
+    # shapes are host objects and work without a device; the simulation needs a context
+    from maxwell_b200 import assembly as asm
+    api = asm.gpu_api()
+    s = api.intersection([api.cylinder(0.4, (0, 0, 1), (0, 0, 0)), api.slab(0.8, (0, 0, 1), (0, 0, 0))])
+    assert s.func((0.0, 0.0, 0.0)) > 0 > s.func((0.0, 0.0, 0.45))
+    with pytest.raises(asm.AssemblyError):
+        api.sim(None, 4)
 
 
 def test_no_cpu_fallback(mx):
@@ -48,7 +65,7 @@ def test_product_never_imports_oracle():
     for base in ("maxwell_b200", "include"):
         for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
             for f in files:
-                if f.endswith((".py", ".cu", ".h", ".hpp", ".cpp")):
+                if f.endswith((".py", ".cu", ".cuh", ".inc", ".h", ".hpp", ".cpp")):
                     txt = open(os.path.join(dirpath, f), errors="ignore").read()
                     if re.search(r"(from|import)\s+oracle|liboracle|mxo_", txt):
                         bad.append(os.path.join(dirpath, f))

@@ -1,0 +1,221 @@
+"""CPU replay of the operator assembly against the oracle.
+
+maxwell_b200/csrc/mxg_yee.h, mxg_shape.h, mxg_asm_impl.h and mxg_asm_api.inc hold the row generators, the CRS algebra,
+the cut-cell fraction rules and the C entry points as host/device code. The product compiles them into CUDA kernels
+(mxg_asm.cu); this test compiles the very same sources with plain loops (tests/cpp/asm_replay.cpp, symbols mxr_*) and
+checks every map, fraction array and operator bit for bit against the oracle, so that the GPU run only has to confirm
+that the device arithmetic rounds like the host's.
+"""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from maxwell_b200 import assembly as asm
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(ROOT, "maxwell_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def api():
+    out_dir = os.path.join(HERE, "cpp", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libasm_replay.so")
+    src = os.path.join(HERE, "cpp", "asm_replay.cpp")
+    deps = [src] + [os.path.join(CSRC, f) for f in ("mxg_yee.h", "mxg_shape.h", "mxg_asm_impl.h", "mxg_asm_api.inc")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall", "-Wno-sign-compare",
+                               "-shared", "-I", CSRC, "-o", so, src])
+    lib = C.CDLL(so)
+    lib.mxr_last_error.restype = C.c_char_p
+    return asm.AssemblyAPI(lib, "mxr_", lib.mxr_last_error)
+
+
+# ---- the same geometry built twice: oracle shapes and product shapes -------------------------------------------------
+def both(api, build):
+    return build(orc.Shape), build(api)
+
+
+def pillbox_shape(S):
+    return S.intersection([S.cylinder(0.4, (0, 0, 1), (0, 0, 0)), S.slab(0.8, (0, 0, 1), (0, 0, 0))])
+
+
+def crabcav_shape(S, num_cells=4, cell_len=2.0 * 0.0192, cav_rad=0.04719, iris_rad=0.015, cav_rho=0.0136, iris_rho=0.00331):
+    """example/crabcav.py:13-66, as oracle.crabcav_shape builds it."""
+    rho_sum = cav_rho + iris_rho
+    rad_diff = cav_rad - iris_rad
+    half2 = 0.25 * cell_len * cell_len
+    diff2 = (rad_diff - rho_sum) ** 2
+    cos_t = (rho_sum - rad_diff) * rho_sum
+    cos_t += math.sqrt(half2 * (diff2 - rho_sum * rho_sum + half2))
+    cos_t /= half2 + diff2
+    theta = math.acos(cos_t)
+    sin_t = math.sqrt(1 - cos_t * cos_t)
+    cot_t = 1.0 / (sin_t / cos_t)
+    cone_off = 0.5 * cell_len - iris_rho * sin_t + (iris_rad + iris_rho * (1.0 - cos_t)) * cot_t
+    zhat, o = (0, 0, 1), (0, 0, 0)
+    iris_tube = S.cylinder(iris_rad + iris_rho * (1.0 - cos_t), zhat, o)
+    iris_torus = S.torus(iris_rad + iris_rho, iris_rho, zhat, (0, 0, 0.5 * cell_len))
+    corr_iris_tube = S.subtract(iris_tube, iris_torus)
+    cav_tube = S.cylinder(cav_rad - cav_rho * (1.0 - cos_t), zhat, o)
+    cav_cone = S.cone(theta, zhat, (0, 0, cone_off))
+    cav_torus = S.torus(cav_rad - cav_rho, cav_rho, zhat, o)
+    pre_cav = S.intersection([cav_cone, cav_tube])
+    half_cell = S.union([pre_cav, cav_torus, corr_iris_tube])
+    full_cell = S.mirror(half_cell, zhat, o)
+    inf_cells = S.repeat(full_cell, o, zhat, cell_len, num_cells // 2, num_cells // 2)
+    caps = S.slab(float(num_cells) * cell_len, zhat, o)
+    return S.intersection([caps, inf_cells])
+
+
+def tilted_shape(S):
+    """Exercises every placement operation and the remaining primitives."""
+    e = S.ellipsoid((0.05, -0.02, 0.01), (0.33, 0.21, 0.27))
+    e.rotate((1, 2, 3), 0.7)
+    c = S.cylinder(0.15, (1, 1, 0), (0.1, 0.0, -0.05))
+    c.rotate((0, 1, 0), -0.4, pivot=(0.2, 0.1, 0.0))
+    s = S.sphere(0.2, (-0.15, 0.1, 0.05))
+    s.scale((1.0, 0.5, 2.0), origin=(-0.1, 0.0, 0.0))
+    h = S.halfspace((0.0, 0.0, 0.12), (0.1, -0.2, -1.0))
+    t = S.torus(0.22, 0.06, (0, 1, 1), (0.0, 0.05, 0.0))
+    t.reflect((1, 0, 0), (0.03, 0, 0))
+    u = S.union([e, c, s, t])
+    u.translate((0.01, 0.02, -0.03))
+    k = S.cone(0.5, (0, 0, 1), (0.0, 0.0, -0.3))
+    k.invert()
+    return S.intersection([u, h, k])
+
+
+SHAPES = {"pillbox": pillbox_shape, "crabcav": crabcav_shape, "tilted": tilted_shape}
+
+
+@pytest.mark.parametrize("name", sorted(SHAPES))
+def test_shape_function_and_gradient_match_the_oracle(api, name):
+    so, sp = both(api, SHAPES[name])
+    rng = np.random.default_rng(7)
+    scale = 0.09 if name == "crabcav" else 0.6
+    pts = rng.uniform(-scale, scale, size=(400, 3))
+    for p in pts:
+        assert so.func(p) == sp.func(p)
+        assert np.array_equal(np.asarray(so.grad(p)), sp.grad(p))
+
+
+def make_pair(api, n, origin, size, shape=None, lower=None, upper=None, phase_shifts=None, literal=False, use_host_fracs=False):
+    so = sp = None
+    if shape is not None:
+        so, sp = both(api, shape)
+    o = orc.Sim(n, origin=origin, size=size, lower=lower, upper=upper, phase_shifts=phase_shifts, pec=so,
+                literal_upper_periodic_e=literal)
+    p = api.sim(None, n, origin=origin, size=size, lower=lower, upper=upper, phase_shifts=phase_shifts,
+                literal_upper_periodic_e=literal)
+    if shape is not None:
+        if use_host_fracs:
+            for f in asm.FIELDS:
+                p.set_pec_fractions(f, o.full_fracs(f))
+        else:
+            p.set_pec_shape(sp)
+    p.setup()
+    return o, p
+
+
+def crab_grid(cell_res=4, pad=2, num_cells=4, cell_len=2.0 * 0.0192, cav_rad=0.04719):
+    delta = cell_len / float(cell_res)
+    nz = num_cells * cell_res + 2 * pad
+    lz = float(nz) * delta
+    nx = 2 * (int(math.ceil(cav_rad / delta)) + pad)
+    lx = float(nx) * delta
+    return (nx, nx, nz), (-0.5 * lx, -0.5 * lx, -0.5 * lz), (lx, lx, lz)
+
+
+CASES = {
+    "vacuum": dict(n=6, origin=(0.0,) * 3, size=(1.0,) * 3),
+    "vacuum-literal": dict(n=5, origin=(0.0,) * 3, size=(1.0,) * 3, literal=True),
+    "vacuum-bloch": dict(n=(5, 6, 4), origin=(0.0,) * 3, size=(1.0, 1.2, 0.8), phase_shifts=(0.3, -0.7, 1.1)),
+    "pillbox": dict(n=12, origin=(-0.5,) * 3, size=(1.0,) * 3, shape=pillbox_shape),
+    "pillbox-hostfracs": dict(n=10, origin=(-0.5,) * 3, size=(1.0,) * 3, shape=pillbox_shape, use_host_fracs=True),
+    "walls": dict(n=(6, 5, 7), origin=(0.0,) * 3, size=(0.5,) * 3, lower=(orc.PEC, orc.PMC, orc.PEC), upper=(orc.PEC,) * 3,
+                  shape=lambda S: S.sphere(0.49, (0, 0, 0))),
+    "walls-mixed": dict(n=6, origin=(0.0,) * 3, size=(1.0,) * 3, lower=(orc.PMC, orc.PERIODIC, orc.PEC),
+                        upper=(orc.PEC, orc.PERIODIC, orc.PMC)),
+    "tilted": dict(n=9, origin=(-0.5,) * 3, size=(1.0,) * 3, shape=tilted_shape),
+    "crabcav": dict(zip(("n", "origin", "size"), crab_grid()), shape=crabcav_shape),
+    "bloch-pec": dict(n=(8, 8, 6), origin=(-0.5, -0.5, 0.0), size=(1.0, 1.0, 0.7), phase_shifts=(0.0, 0.0, 2.0 * math.pi / 3.0),
+                      shape=lambda S: S.union([S.intersection([S.cylinder(0.4, (0, 0, 1), (0, 0, 0)), S.slab(0.4, (0, 0, 1), (0, 0, 0.35))]),
+                                               S.cylinder(0.15, (0, 0, 1), (0, 0, 0))])),
+}
+OPS = ("curlE", "curlB", "divB", "gradPsi", "dmA", "dmL", "dmVInv", "mRhs", "curlCurl", "gradDiv", "vecLapl", "scaLapl")
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_maps_fractions_and_operators_match_the_oracle_bit_for_bit(api, case):
+    o, p = make_pair(api, **CASES[case])
+    for f in asm.FIELDS:
+        assert np.array_equal(o.map(f), p.map(f)), f
+        assert o.num_global(f) == p.num_global(f)
+        ref = o.full_fracs(f)
+        if ref is not None:
+            assert np.array_equal(ref, p.fracs(f)), f
+    for name in OPS:
+        a, b = o.op(name), p.op(name)
+        assert (a.nrows, a.ncols, a.nnz, a.is_complex) == (b.nrows, b.ncols, b.nnz, b.is_complex), name
+        for x, y in zip(a.arrays(), b.arrays()):
+            assert np.array_equal(x, y), name
+    # real-valued build of a Bloch problem keeps the real parts (MxUtil.hpp:58-62)
+    if CASES[case].get("phase_shifts"):
+        for x, y in zip(o.op("curlCurl", is_complex=False).arrays(), p.op("curlCurl", is_complex=False).arrays()):
+            assert np.array_equal(x, y)
+
+
+def test_crs_algebra_entry_points(api):
+    o, p = make_pair(api, **CASES["pillbox"])
+    ce, cb, dl = p.op("curlE"), p.op("curlB"), p.op("dmL")
+    cc = ce @ (dl @ cb)
+    ref = o.op("curlCurl")
+    for x, y in zip(ref.arrays(), cc.arrays()):
+        assert np.array_equal(x, y)
+    assert (cc.row_field, cc.col_field) == ("bfield", "bfield")
+    gd = p.op("gradDiv")
+    vl = cc.add(1.0, gd, -1.0, purge=True)
+    for x, y in zip(o.op("vecLapl").arrays(), vl.arrays()):
+        assert np.array_equal(x, y)
+    unpurged = cc.add(1.0, gd, -1.0)
+    assert unpurged.nnz >= vl.nnz
+    for x, y in zip(vl.arrays(), unpurged.purge().arrays()):
+        assert np.array_equal(x, y)
+    ref_sum = o.op("curlCurl").add(2.0, o.op("gradDiv"), -0.5)
+    for x, y in zip(ref_sum.arrays(), cc.add(2.0, gd, -0.5).arrays()):
+        assert np.array_equal(x, y)
+    # row slices come back rebased
+    rp, col, val = cc.arrays(100, 180)
+    frp, fcol, fval = cc.arrays()
+    assert np.array_equal(rp, frp[100:181] - frp[100]) and np.array_equal(col, fcol[frp[100]:frp[180]])
+    assert np.array_equal(val, fval[frp[100]:frp[180]])
+    cc.scale(-2.0)
+    assert np.array_equal(cc.arrays()[2], -2.0 * fval)
+    with pytest.raises(asm.AssemblyError):
+        ce @ ce      # shapes do not chain
+    with pytest.raises(asm.AssemblyError):
+        p.op("noSuchOperator")
+
+
+def test_dielectric_chain_with_a_host_generated_inverse_permittivity(api):
+    """MxYeeFitInvEps stays on the host; its matrix is uploaded and the chain around it runs here."""
+    n = 8
+    diel = orc.Shape.sphere(0.37, (0, 0, 0))
+    o = orc.Sim(n, origin=(-0.5,) * 3, size=(1.0,) * 3, pec=orc.Shape.sphere(0.49, (0, 0, 0)), dielectrics=[(diel, orc.SAPPHIRE)])
+    p = api.sim(None, n, origin=(-0.5,) * 3, size=(1.0,) * 3)
+    p.set_pec_shape(api.sphere(0.49, (0, 0, 0))).setup()
+    ie, iv = o.op("invEps"), o.op("invEpsVolAve")
+    d_ie = p.upload("efield", "efield", *ie.arrays(), ncols=ie.ncols)
+    d_iv = p.upload("psifield", "psifield", *iv.arrays(), ncols=iv.ncols)
+    for name in ("curlCurl", "gradDiv", "vecLapl"):
+        got = p.op(name, inv_eps=d_ie, inv_eps_vol_ave=d_iv)
+        for x, y in zip(o.op(name).arrays(), got.arrays()):
+            assert np.array_equal(x, y), name

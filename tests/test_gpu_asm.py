@@ -1,0 +1,126 @@
+"""Operator assembly on the GPU against the oracle: cut-cell fractions, DOF maps and every named
+operator must come back bit for bit, and an operator assembled on the device must apply exactly like the one uploaded
+from the oracle's host CSR. The cases are those of the CPU replay (tests/test_asm_replay.py), which pins the same
+sources without a GPU; here the CUDA kernels run.
+"""
+import numpy as np
+import pytest
+
+from test_asm_replay import CASES, OPS, both, pillbox_shape, crabcav_shape, crab_grid  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_pair(asm, ctx, orc, n, origin, size, shape=None, lower=None, upper=None, phase_shifts=None, literal=False,
+             use_host_fracs=False):
+    api = asm.gpu_api()
+    so = sp = None
+    if shape is not None:
+        so, sp = both(api, shape)
+    o = orc.Sim(n, origin=origin, size=size, lower=lower, upper=upper, phase_shifts=phase_shifts, pec=so,
+                literal_upper_periodic_e=literal)
+    p = asm.gpu_sim(ctx, n, origin=origin, size=size, lower=lower, upper=upper, phase_shifts=phase_shifts,
+                    literal_upper_periodic_e=literal)
+    if shape is not None:
+        if use_host_fracs:
+            for f in asm.FIELDS:
+                p.set_pec_fractions(f, o.full_fracs(f))
+        else:
+            p.set_pec_shape(sp)
+    p.setup()
+    return o, p
+
+
+@pytest.fixture(scope="module")
+def asm(mx):
+    from maxwell_b200 import assembly
+    return assembly
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_device_assembly_matches_the_oracle_bit_for_bit(asm, ctx, orc, case):
+    o, p = gpu_pair(asm, ctx, orc, **CASES[case])
+    for f in asm.FIELDS:
+        assert np.array_equal(o.map(f), p.map(f)), f
+        ref = o.full_fracs(f)
+        if ref is not None:
+            got = p.fracs(f)
+            bad = np.flatnonzero(ref != got)
+            assert bad.size == 0, "%s: %d of %d fractions differ, first %r vs %r" % (f, bad.size, ref.size, ref[bad[:1]], got[bad[:1]])
+    for name in OPS:
+        a, b = o.op(name), p.op(name)
+        assert (a.nrows, a.ncols, a.nnz, a.is_complex) == (b.nrows, b.ncols, b.nnz, b.is_complex), name
+        for x, y in zip(a.arrays(), b.arrays()):
+            assert np.array_equal(x, y), name
+
+
+def test_prefix_scan_and_products_at_a_size_that_spans_many_blocks(asm, ctx, orc):
+    """40^3 pillbox: 200 k rows, several scan chunks per pass, product rows of every length."""
+    o, p = gpu_pair(asm, ctx, orc, 40, (-0.5,) * 3, (1.0,) * 3, shape=pillbox_shape)
+    for f in asm.FIELDS:
+        assert np.array_equal(o.map(f), p.map(f)), f
+        assert np.array_equal(o.full_fracs(f), p.fracs(f)), f
+    for name in ("curlCurl", "vecLapl", "scaLapl"):
+        for x, y in zip(o.op(name).arrays(), p.op(name).arrays()):
+            assert np.array_equal(x, y), name
+
+
+def test_device_assembled_operator_applies_like_the_uploaded_one(asm, mx, ctx, orc):
+    o, p = gpu_pair(asm, ctx, orc, 24, (-0.5,) * 3, (1.0,) * 3, shape=pillbox_shape)
+    bmap = asm.make_map(p, "bfield")
+    assert np.array_equal(bmap.gids, o.map("bfield"))
+    A = asm.to_crs(p.op("curlCurl"), bmap, bmap)
+    ref = o.op("curlCurl")
+    x = mx.MxMultiVector(bmap, 3)
+    x.random(4242)
+    y = mx.MxMultiVector(bmap, 3)
+    A.apply(x, y)
+    assert np.array_equal(ref.apply(x.to_host()), y.to_host())
+    st = A.stats()
+    assert st["rows"] == ref.nrows and st["nnz"] == ref.nnz and st["dict_rows"] > 0
+    # rectangular operator on two maps, sliced-ELL path
+    pmap = asm.make_map(p, "psifield")
+    D = asm.to_crs(p.op("divB"), pmap, bmap)
+    z = mx.MxMultiVector(pmap, 3)
+    D.apply(x, z)
+    assert np.array_equal(o.op("divB").apply(x.to_host()), z.to_host())
+
+
+def test_complex_bloch_operator_assembled_on_the_device(asm, mx, ctx, orc):
+    o, p = gpu_pair(asm, ctx, orc, **CASES["bloch-pec"])
+    bmap = asm.make_map(p, "bfield")
+    A = asm.to_crs(p.op("vecLapl"), bmap, bmap)
+    x = mx.MxMultiVector(bmap, 2, is_complex=True)
+    x.random(99)
+    y = mx.MxMultiVector(bmap, 2, is_complex=True)
+    A.apply(x, y)
+    assert np.array_equal(o.op("vecLapl").apply(x.to_host()), y.to_host())
+
+
+def test_dielectric_chain_around_an_uploaded_inverse_permittivity(asm, ctx, orc):
+    n = 10
+    o = orc.Sim(n, origin=(-0.5,) * 3, size=(1.0,) * 3, pec=orc.Shape.sphere(0.49, (0, 0, 0)),
+                dielectrics=[(orc.Shape.sphere(0.37, (0, 0, 0)), orc.SAPPHIRE)])
+    api = asm.gpu_api()
+    p = asm.gpu_sim(ctx, n, origin=(-0.5,) * 3, size=(1.0,) * 3)
+    p.set_pec_shape(api.sphere(0.49, (0, 0, 0))).setup()
+    ie, iv = o.op("invEps"), o.op("invEpsVolAve")
+    d_ie = p.upload("efield", "efield", *ie.arrays(), ncols=ie.ncols)
+    d_iv = p.upload("psifield", "psifield", *iv.arrays(), ncols=iv.ncols)
+    for name in ("curlCurl", "vecLapl"):
+        for x, y in zip(o.op(name).arrays(), p.op(name, inv_eps=d_ie, inv_eps_vol_ave=d_iv).arrays()):
+            assert np.array_equal(x, y), name
+
+
+def test_errors_are_reported_not_swallowed(asm, ctx):
+    api = asm.gpu_api()
+    p = asm.gpu_sim(ctx, 6)
+    with pytest.raises(asm.AssemblyError):
+        p.map("bfield")                      # before setup
+    p.setup()
+    with pytest.raises(asm.AssemblyError):
+        p.op("curlE") @ p.op("curlE")
+    with pytest.raises(asm.AssemblyError):
+        api.sim(ctx.h, (0, 4, 4))
+    with pytest.raises(asm.AssemblyError):
+        api.sim(None, 4)                     # no context: the product never runs without a device
