@@ -89,6 +89,10 @@ int mxg_dcsr_multiply(const mxg_dcsr* a, const mxg_dcsr* b, mxg_dcsr** out);    
 int mxg_dcsr_add(const mxg_dcsr* a, const double sa[2], const mxg_dcsr* b, const double sb[2], int purge, mxg_dcsr** out); /* :401-430 */
 int mxg_dcsr_purge(const mxg_dcsr* a, mxg_dcsr** out);                                           /* MxCrsMatrix.cpp:84-117 */
 int mxg_dcsr_scale(mxg_dcsr* a, const double s[2]);
+int mxg_dcsr_transpose(const mxg_dcsr* a, mxg_dcsr** out); /* conjugate transpose, rows sorted by column */
+/* MxGridFieldInterpolator (MxGridFieldInterpolator.cpp:28-122): `field` of sim_from interpolated at the DOFs of sim_to --
+ * the refiners / coarseners of MxGeoMultigridPrec (MxGeoMultigridPrec.cpp:98-240). Rows on sim_to, columns on sim_from. */
+int mxg_sim_interpolator(mxg_sim* sim_from, mxg_sim* sim_to, const char* field, int is_complex, mxg_dcsr** out);
 /* out = {rows, columns, entries, is_complex, row field, column field}; fields 0 B, 1 E, 2 psi, -1 unknown */
 int mxg_dcsr_shape(const mxg_dcsr* a, int64_t out[6]);
 /* rows [row_begin, row_end) to the host; rowptr is rebased to 0; col / vals may be NULL */

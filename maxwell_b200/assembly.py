@@ -45,6 +45,8 @@ class AssemblyAPI:
             "dcsr_add": [vp, d3, vp, d3, i32, pvp],
             "dcsr_purge": [vp, pvp],
             "dcsr_scale": [vp, d3],
+            "dcsr_transpose": [vp, pvp],
+            "sim_interpolator": [vp, vp, C.c_char_p, i32, pvp],
             "dcsr_shape": [vp, C.POINTER(i64)],
             "dcsr_download": [vp, i64, i64, vp, vp, vp],
             "dcsr_destroy": [vp],
@@ -239,6 +241,19 @@ class Sim:
                       inv_eps_vol_ave.handle if inv_eps_vol_ave is not None else None, C.byref(h))
         return DeviceCsr(self, h)
 
+    def interpolator_from(self, coarse, field="bfield", is_complex=None):
+        """MxGridFieldInterpolator: `field` of the simulation `coarse` interpolated at this simulation's DOFs."""
+        if not self._setup:
+            self.setup()
+        if not coarse._setup:
+            coarse.setup()
+        cplx = self.is_complex if is_complex is None else bool(is_complex)
+        h = C.c_void_p()
+        self.api.call("sim_interpolator", coarse.handle, self.handle, field.encode(), 1 if cplx else 0, C.byref(h))
+        m = DeviceCsr(self, h)
+        m.col_sim = coarse
+        return m
+
     def upload(self, row_field, col_field, rowptr, col, val, ncols):
         """Host CSR with local column indices -> device (operators still generated on the host, e.g. the dielectric invEps)."""
         rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
@@ -291,6 +306,16 @@ class DeviceCsr:
         self.api.call("dcsr_add", self.handle, _d3((sa.real, sa.imag, 0)), other.handle, _d3((sb.real, sb.imag, 0)),
                       1 if purge else 0, C.byref(h))
         return DeviceCsr(self.sim, h)
+
+    def transpose(self, scale=None):
+        h = C.c_void_p()
+        self.api.call("dcsr_transpose", self.handle, C.byref(h))
+        t = DeviceCsr(self.sim, h)
+        t.col_sim = self.sim                      # keep both simulations alive
+        t.row_sim = getattr(self, "col_sim", self.sim)
+        if scale is not None:
+            t.scale(scale)
+        return t
 
     def purge(self):
         h = C.c_void_p()
@@ -363,3 +388,107 @@ def to_crs(dcsr, row_map, domain_map, layout=0):
     A = mx.MxCrsMatrix(row_map, domain_map, dcsr.is_complex)
     A.h = h
     return A
+
+
+# ---- example geometries of the reference (example/*.py), written against any shape factory with the method names of
+# AssemblyAPI (the tests hand the same functions the oracle's factory to build the comparison geometry) ---------------
+def pillbox_shape(S, radius=0.4, length=0.8):
+    """example/pillbox.py:14-17 -- Cylinder(R, axis z) intersected with Slab(thickness, normal z)."""
+    return S.intersection([S.cylinder(radius, (0, 0, 1), (0, 0, 0)), S.slab(length, (0, 0, 1), (0, 0, 0))])
+
+
+def crabcav_shape(S, num_cells=4, cell_len=2.0 * 0.0192, cav_rad=0.04719, iris_rad=0.015, cav_rho=0.0136, iris_rho=0.00331):
+    """example/crabcav.py:13-66 -- the 4-cell crab cavity as CSG: per half cell (cone & tube) | equator torus |
+    (iris tube - iris torus), mirrored in z = 0, repeated along z and capped by a slab."""
+    import math
+    rho_sum = cav_rho + iris_rho
+    rad_diff = cav_rad - iris_rad
+    half2 = 0.25 * cell_len * cell_len
+    diff2 = (rad_diff - rho_sum) ** 2
+    cos_t = (rho_sum - rad_diff) * rho_sum
+    cos_t += math.sqrt(half2 * (diff2 - rho_sum * rho_sum + half2))
+    cos_t /= half2 + diff2
+    theta = math.acos(cos_t)
+    sin_t = math.sqrt(1 - cos_t * cos_t)
+    cot_t = 1.0 / (sin_t / cos_t)
+    cone_off = 0.5 * cell_len - iris_rho * sin_t + (iris_rad + iris_rho * (1.0 - cos_t)) * cot_t
+    zhat, o = (0, 0, 1), (0, 0, 0)
+    iris_tube = S.cylinder(iris_rad + iris_rho * (1.0 - cos_t), zhat, o)
+    iris_torus = S.torus(iris_rad + iris_rho, iris_rho, zhat, (0, 0, 0.5 * cell_len))
+    corr_iris_tube = S.subtract(iris_tube, iris_torus)
+    cav_tube = S.cylinder(cav_rad - cav_rho * (1.0 - cos_t), zhat, o)
+    cav_cone = S.cone(theta, zhat, (0, 0, cone_off))
+    cav_torus = S.torus(cav_rad - cav_rho, cav_rho, zhat, o)
+    pre_cav = S.intersection([cav_cone, cav_tube])
+    half_cell = S.union([pre_cav, cav_torus, corr_iris_tube])
+    full_cell = S.mirror(half_cell, zhat, o)
+    inf_cells = S.repeat(full_cell, o, zhat, cell_len, num_cells // 2, num_cells // 2)
+    caps = S.slab(float(num_cells) * cell_len, zhat, o)
+    return S.intersection([caps, inf_cells])
+
+
+def crabcav_grid(cell_res=10, pad=2, num_cells=4, cell_len=2.0 * 0.0192, cav_rad=0.04719):
+    """example/crabcav.py:69-91: cell_res cells per cavity cell along z plus `pad` cells of metal around -> (n, origin, size)."""
+    import math
+    delta = cell_len / float(cell_res)
+    nz = num_cells * cell_res + 2 * pad
+    lz = float(nz) * delta
+    nx = 2 * (int(math.ceil(cav_rad / delta)) + pad)
+    lx = float(nx) * delta
+    return (nx, nx, nz), (-0.5 * lx, -0.5 * lx, -0.5 * lz), (lx, lx, lz)
+
+
+def example_sim(ctx, workload, n):
+    """The PEC-only workloads of bench.py as device simulations (set up, ready for op())."""
+    api = gpu_api()
+    if workload == "pillbox":
+        sim = gpu_sim(ctx, n, origin=(-0.5,) * 3, size=(1.0,) * 3)
+        sim.set_pec_shape(pillbox_shape(api))
+    elif workload == "vacuum":
+        sim = gpu_sim(ctx, n, origin=(0.0,) * 3, size=(1.0,) * 3)
+    elif workload == "crabcav":
+        nn, origin, size = crabcav_grid(cell_res=max(2, (n - 4) // 4))
+        sim = gpu_sim(ctx, nn, origin=origin, size=size)
+        sim.set_pec_shape(crabcav_shape(api))
+    else:
+        raise AssemblyError("workload %r has dielectrics: its inverse-permittivity operator is host-generated "
+                            "(upload it with Sim.upload and pass inv_eps= to op())" % workload)
+    return sim.setup()
+
+
+class EigenProblem:
+    """Everything MxSolver needs for the projected eigensolve, assembled on the device: the re-discretisation hierarchy
+    of MxEMSimHierarchy (MxEMSimHierarchy.cpp:37-76) for the vector and the scalar Laplacian, trilinear transfers
+    (restriction = P^T / 8), divB / gradPsi / curlCurl on the fine grid and the mass diagonal dmA.
+
+    sims: device simulations, fine to coarse. cuts(level, field, gids, num_global) -> (begin, end) selects this rank's
+    rows of a field map (x-slabs); None = the whole map (one rank)."""
+
+    def __init__(self, ctx, sims, cuts=None, is_complex=False):
+        import maxwell_b200 as mx
+        self.sims = sims
+        rng = {}
+        for l, s in enumerate(sims):
+            for f in ("bfield", "psifield"):
+                g = s.map(f)
+                rng[l, f] = (0, len(g)) if cuts is None else cuts(l, f, g, s.num_global(f))
+        self.bmaps = [make_map(s, "bfield", *rng[l, "bfield"]) for l, s in enumerate(sims)]
+        self.pmaps = [make_map(s, "psifield", *rng[l, "psifield"]) for l, s in enumerate(sims)]
+        cx = is_complex
+        self.vops = [to_crs(s.op("vecLapl", cx), self.bmaps[l], self.bmaps[l]) for l, s in enumerate(sims)]
+        self.sops = [to_crs(s.op("scaLapl", cx), self.pmaps[l], self.pmaps[l]) for l, s in enumerate(sims)]
+        self.Rb, self.Pb, self.Rp, self.Pp = [], [], [], []
+        for l in range(len(sims) - 1):
+            for f, maps, Rl, Pl in (("bfield", self.bmaps, self.Rb, self.Pb), ("psifield", self.pmaps, self.Rp, self.Pp)):
+                p = sims[l].interpolator_from(sims[l + 1], f, cx)
+                Pl.append(to_crs(p, maps[l], maps[l + 1]))
+                Rl.append(to_crs(p.transpose(scale=0.125), maps[l + 1], maps[l]))
+        s0 = sims[0]
+        self.divB = to_crs(s0.op("divB", cx), self.pmaps[0], self.bmaps[0])
+        self.gradPsi = to_crs(s0.op("gradPsi", cx), self.bmaps[0], self.pmaps[0])
+        self.curlCurl = to_crs(s0.op("curlCurl", cx), self.bmaps[0], self.bmaps[0])
+        b0, b1 = rng[0, "bfield"]
+        fa = s0.op("dmA", False).arrays(b0, b1)[2]
+        self.m_diag = mx.MxMultiVector(self.bmaps[0], 1, cx)
+        self.m_diag.from_host(fa.astype(np.complex128) if cx else fa)
+        self.fracs = fa

@@ -170,6 +170,11 @@ struct DeviceExec {
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // the source may be a stack temporary
     if (e != cudaSuccess) fail("host -> device copy of the operator assembly", e);
   }
+  void zero(void* p, size_t bytes) {
+    if (!bytes) return;
+    const cudaError_t e = cudaMemsetAsync(p, 0, bytes, ctx->stream);
+    if (e != cudaSuccess) fail("device memset of the operator assembly", e);
+  }
   void sync() {
     const cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) fail("operator assembly", e);
@@ -204,12 +209,14 @@ int mxg_crs_create_from_dcsr(mxg_map* row_map, mxg_map* domain_map, const mxg_dc
   const int rf = A->rowField(), cf = A->colField();
   MXG_REQUIRE(rf >= 0 && cf >= 0, "mxg_crs_create_from_dcsr: the matrix does not know which fields its rows and columns live on");
   try {
-    mxa::Assembler<DeviceExec>& as = *A->sim->as;
-    MXG_REQUIRE(domain_map->nGlobal == as.numGlobal(cf) && row_map->nGlobal == as.numGlobal(rf),
+    mxa::Assembler<DeviceExec>& asR = *A->rows()->as;
+    mxa::Assembler<DeviceExec>& asC = *A->cols()->as;
+    MXG_REQUIRE(domain_map->nGlobal == asC.numGlobal(cf) && row_map->nGlobal == asR.numGlobal(rf),
                 "mxg_crs_create_from_dcsr: maps do not span the simulation's GID space");
-    std::vector<int64_t> rowG(static_cast<size_t>(as.mapSize(rf)), 0), colG(static_cast<size_t>(as.mapSize(cf)), 0);
-    as.copyMap(rf, rowG.data());
-    as.copyMap(cf, colG.data());
+    MXG_REQUIRE(asR.mapSize(rf) == A->nrows() && asC.mapSize(cf) == A->ncols(), "mxg_crs_create_from_dcsr: the matrix does not live on these field maps");
+    std::vector<int64_t> rowG(static_cast<size_t>(asR.mapSize(rf)), 0), colG(static_cast<size_t>(asC.mapSize(cf)), 0);
+    asR.copyMap(rf, rowG.data());
+    asC.copyMap(cf, colG.data());
     // the rank's rows: one contiguous run of the field map (x-slabs)
     int64_t r0 = 0, r1 = 0;
     if (row_map->nLocal > 0) {

@@ -281,6 +281,38 @@ class Assembler {
     return m;
   }
 
+  // (conjugate) transpose, rows sorted by column
+  template <class S>
+  Csr<S> transpose(const Csr<S>& A) {
+    Csr<S> T;
+    T.nrows = A.ncols; T.ncols = A.nrows; T.nnz = A.nnz;
+    T.rowField = A.colField; T.colField = A.rowField;
+    int32_t* cnt = x_.template alloc<int32_t>(T.nrows > 0 ? T.nrows : 1);
+    x_.zero(cnt, size_t(T.nrows) * sizeof(int32_t));
+    x_.forEach(A.nnz, mxy::TransposeCount{A.col, cnt});
+    T.rowptr = x_.template alloc<int64_t>(T.nrows + 1);
+    x_.scan(cnt, T.rowptr, T.nrows);
+    x_.zero(cnt, size_t(T.nrows) * sizeof(int32_t));
+    T.col = x_.template alloc<int32_t>(T.nnz > 0 ? T.nnz : 1);
+    T.val = x_.template alloc<S>(T.nnz > 0 ? T.nnz : 1);
+    x_.forEach(A.nrows, mxy::TransposeFill<S>{A.view(), T.rowptr, cnt, T.col, T.val});
+    x_.forEach(T.nrows, mxy::SortRowInPlace<S>{T.rowptr, T.col, T.val});
+    x_.free(cnt);
+    return T;
+  }
+
+  // MxGridFieldInterpolator.cpp:28-122: `field` of the simulation `from` interpolated at the DOFs of this simulation
+  // (rows: this simulation's map, columns: from's map). Both live on the same executor.
+  template <class S>
+  Csr<S> interpolatorFrom(Assembler& from, int field) {
+    requireSetUp();
+    from.requireSetUp();
+    Csr<S> m = buildRows<S>(h_.f[field].nLoc, from.h_.f[field].nLoc, mxy::InterpRow<S>{from.dSim_, dSim_, field});
+    m.rowField = field;
+    m.colField = field;
+    return m;
+  }
+
   // ---- generators and chains ---------------------------------------------------------------------------------
   template <class S>
   Csr<S> generate(int op, int fracField = 0, bool inverse = false, double minFrac = 0.0) {

@@ -463,6 +463,117 @@ struct FillRows {
   }
 };
 
+// ---- grid transfers and transposition --------------------------------------------------------------------------------
+MXY_HD double divReal(double v, double s) { return v / s; }
+MXY_HD Cx divReal(Cx v, double s) { return {v.re / s, v.im / s}; }   // what (v + 0i) / (s + 0i) evaluates to for s > 0
+MXY_HD double conjS(double v) { return v; }
+MXY_HD Cx conjS(Cx v) { return {v.re, -v.im}; }
+MXY_HD double floorD(double v) {
+#if defined(__CUDA_ARCH__)
+  return ::floor(v);
+#else
+  return __builtin_floor(v);
+#endif
+}
+MXY_HD int32_t fetchInc(int32_t* p) {
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(p, 1);
+#else
+  return __atomic_fetch_add(p, 1, __ATOMIC_RELAXED);
+#endif
+}
+
+// MxGridFieldInterpolator.cpp:28-65 (stencil), :68-122 (insertion, row-sum normalisation): (tri)linear interpolation of
+// a field of the `from` grid at the component positions of the `to` grid. Entries whose column is not a DOF are
+// dropped, then the row is divided by the sum of the magnitudes of what is left. (The reference's unset stencil point
+// and never-zeroed row-sum accumulator are not reproduced)
+template <class S>
+struct InterpRow {
+  static constexpr int kMax = 8;
+  const Sim* from;
+  const Sim* to;
+  int kind;
+  MXY_HD int operator()(int64_t row, int32_t* cols, S* vals) const {
+    const Sim& sf = *from;
+    const Sim& st = *to;
+    const Field& ff = sf.f[kind];
+    const Field& tf = st.f[kind];
+    int tcell[3], comp;
+    cellCompOf(st, tf, tf.gids[row], tcell, comp);
+    double point[3];
+    int c0[3];
+    for (int i = 0; i < 3; ++i) {
+      point[i] = (st.g.origin[i] + double(tcell[i]) * st.g.d[i]) + tf.xi[comp][i];
+      c0[i] = int(floorD((point[i] - ff.xi[comp][i] - sf.g.origin[i]) / sf.g.d[i]));
+    }
+    double sum = 0.0;
+    int n = 0;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 2; ++c) {
+          const int cell[3] = {c0[0] + a, c0[1] + b, c0[2] + c};
+          double w = 1.0;
+          bool inRange = true;
+          for (int i = 0; i < 3; ++i) {
+            const double p0 = (sf.g.origin[i] + double(cell[i]) * sf.g.d[i]) + ff.xi[comp][i];
+            w *= 1.0 - absD(point[i] - p0) / sf.g.d[i];
+            if (cell[i] < -1 || cell[i] > sf.g.N[i] + 1) inRange = false;
+          }
+          if (!inRange) continue;
+          const int32_t l = ff.lidOf[gidOf(sf.g, ff, comp, cell)];
+          if (l < 0) continue;
+          cols[n] = l;
+          vals[n] = fromParts<S>(w, 0.0);
+          ++n;
+          sum += absD(w);
+        }
+    if (sum > 0)
+      for (int e = 0; e < n; ++e) vals[e] = divReal(vals[e], sum);
+    return flushRow<S>(n, cols, vals);
+  }
+};
+
+// (conjugate) transpose in three passes: column counts, scattered fill, then every row sorted by column so that the
+// result does not depend on the order in which threads claimed their slots
+struct TransposeCount {
+  const int32_t* col;
+  int32_t* count;
+  MXY_HD void operator()(int64_t q) const { fetchInc(count + col[q]); }
+};
+template <class S>
+struct TransposeFill {
+  CsrView<S> A;
+  const int64_t* tptr;
+  int32_t* fill;
+  int32_t* tcol;
+  S* tval;
+  MXY_HD void operator()(int64_t i) const {
+    for (int64_t p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) {
+      const int32_t j = A.col[p];
+      const int64_t pos = tptr[j] + fetchInc(fill + j);
+      tcol[pos] = int32_t(i);
+      tval[pos] = conjS(A.val[p]);
+    }
+  }
+};
+template <class S>
+struct SortRowInPlace {
+  const int64_t* rowptr;
+  int32_t* col;
+  S* val;
+  MXY_HD void operator()(int64_t i) const {
+    const int64_t b = rowptr[i], e = rowptr[i + 1];
+    for (int64_t k = b + 1; k < e; ++k) {
+      const int32_t c = col[k];
+      const S v = val[k];
+      int64_t j = k - 1;
+      while (j >= b && col[j] > c) { col[j + 1] = col[j]; val[j + 1] = val[j]; --j; }
+      col[j + 1] = c;
+      val[j + 1] = v;
+    }
+  }
+};
+
 // DOF flags of a field over the in-range cells (MxGridField.cpp:256-297: x slow .. z fast, components inner)
 struct MapFlags {
   const Sim* sim;

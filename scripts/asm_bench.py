@@ -52,8 +52,8 @@ def main():
     x.random(12345)
     y = mx.MxMultiVector(bmap, 1)
     A.apply(x, y)
-    yh = y.to_host()
-    out["y_checksum"] = float(np.sum(yh * np.arange(1, yh.size + 1) % 7))
+    yh = y.to_host().reshape(-1)
+    out["y_norm"] = float(np.linalg.norm(yh))
     if with_oracle:
         from oracle import oracle as orc
         t = time.time()
@@ -66,7 +66,7 @@ def main():
         out["curlCurl_csr_bit_exact"] = bool(same)
         out["maps_equal"] = bool(np.array_equal(o.map("bfield"), sim.map("bfield")))
         out["fractions_equal"] = bool(all(np.array_equal(o.full_fracs(f), sim.fracs(f)) for f in asm.FIELDS))
-        out["apply_bit_exact"] = bool(np.array_equal(ref.apply(x.to_host()), yh))
+        out["apply_bit_exact"] = bool(np.array_equal(ref.apply(x.to_host().reshape(-1)), yh))
         out["host_threads"] = orc.lib().mxo_num_threads()
     print(json.dumps(out))
 

@@ -32,6 +32,7 @@ struct HostExec {
   }
   void toHost(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
   void toExec(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
+  void zero(void* p, size_t bytes) { if (bytes) std::memset(p, 0, bytes); }
   void sync() {}
 };
 

@@ -43,36 +43,7 @@ def both(api, build):
     return build(orc.Shape), build(api)
 
 
-def pillbox_shape(S):
-    return S.intersection([S.cylinder(0.4, (0, 0, 1), (0, 0, 0)), S.slab(0.8, (0, 0, 1), (0, 0, 0))])
-
-
-def crabcav_shape(S, num_cells=4, cell_len=2.0 * 0.0192, cav_rad=0.04719, iris_rad=0.015, cav_rho=0.0136, iris_rho=0.00331):
-    """example/crabcav.py:13-66, as oracle.crabcav_shape builds it."""
-    rho_sum = cav_rho + iris_rho
-    rad_diff = cav_rad - iris_rad
-    half2 = 0.25 * cell_len * cell_len
-    diff2 = (rad_diff - rho_sum) ** 2
-    cos_t = (rho_sum - rad_diff) * rho_sum
-    cos_t += math.sqrt(half2 * (diff2 - rho_sum * rho_sum + half2))
-    cos_t /= half2 + diff2
-    theta = math.acos(cos_t)
-    sin_t = math.sqrt(1 - cos_t * cos_t)
-    cot_t = 1.0 / (sin_t / cos_t)
-    cone_off = 0.5 * cell_len - iris_rho * sin_t + (iris_rad + iris_rho * (1.0 - cos_t)) * cot_t
-    zhat, o = (0, 0, 1), (0, 0, 0)
-    iris_tube = S.cylinder(iris_rad + iris_rho * (1.0 - cos_t), zhat, o)
-    iris_torus = S.torus(iris_rad + iris_rho, iris_rho, zhat, (0, 0, 0.5 * cell_len))
-    corr_iris_tube = S.subtract(iris_tube, iris_torus)
-    cav_tube = S.cylinder(cav_rad - cav_rho * (1.0 - cos_t), zhat, o)
-    cav_cone = S.cone(theta, zhat, (0, 0, cone_off))
-    cav_torus = S.torus(cav_rad - cav_rho, cav_rho, zhat, o)
-    pre_cav = S.intersection([cav_cone, cav_tube])
-    half_cell = S.union([pre_cav, cav_torus, corr_iris_tube])
-    full_cell = S.mirror(half_cell, zhat, o)
-    inf_cells = S.repeat(full_cell, o, zhat, cell_len, num_cells // 2, num_cells // 2)
-    caps = S.slab(float(num_cells) * cell_len, zhat, o)
-    return S.intersection([caps, inf_cells])
+pillbox_shape, crabcav_shape = asm.pillbox_shape, asm.crabcav_shape
 
 
 def tilted_shape(S):
@@ -125,13 +96,8 @@ def make_pair(api, n, origin, size, shape=None, lower=None, upper=None, phase_sh
     return o, p
 
 
-def crab_grid(cell_res=4, pad=2, num_cells=4, cell_len=2.0 * 0.0192, cav_rad=0.04719):
-    delta = cell_len / float(cell_res)
-    nz = num_cells * cell_res + 2 * pad
-    lz = float(nz) * delta
-    nx = 2 * (int(math.ceil(cav_rad / delta)) + pad)
-    lx = float(nx) * delta
-    return (nx, nx, nz), (-0.5 * lx, -0.5 * lx, -0.5 * lz), (lx, lx, lz)
+def crab_grid(cell_res=4):
+    return asm.crabcav_grid(cell_res=cell_res)
 
 
 CASES = {
@@ -219,3 +185,27 @@ def test_dielectric_chain_with_a_host_generated_inverse_permittivity(api):
         got = p.op(name, inv_eps=d_ie, inv_eps_vol_ave=d_iv)
         for x, y in zip(o.op(name).arrays(), got.arrays()):
             assert np.array_equal(x, y), name
+
+
+@pytest.mark.parametrize("case", ["pillbox", "vacuum-bloch", "walls"])
+def test_grid_transfers_match_the_oracle(api, case):
+    """Prolongators (MxGridFieldInterpolator) between a grid and the one with half the cells, and the restrictions
+    P^T / 8 the multigrid hierarchy of bench.py uses."""
+    kw = dict(CASES[case])
+    n = kw.pop("n")
+    n = (n,) * 3 if np.isscalar(n) else n
+    fine_n = tuple(2 * (v // 2) for v in n)
+    coarse_n = tuple(v // 2 for v in fine_n)
+    of, pf = make_pair(api, n=fine_n, **kw)
+    oc, pc = make_pair(api, n=coarse_n, **kw)
+    cx = bool(kw.get("phase_shifts"))
+    for field in ("bfield", "psifield"):
+        ref = orc.interpolator(oc, of, field=field, is_complex=cx)
+        got = pf.interpolator_from(pc, field, is_complex=cx)
+        assert (ref.nrows, ref.ncols, ref.nnz) == (got.nrows, got.ncols, got.nnz)
+        for x, y in zip(ref.arrays(), got.arrays()):
+            assert np.array_equal(x, y), field
+        rt, gt = ref.transpose(scale=0.125), got.transpose(scale=0.125)
+        assert (rt.nrows, rt.ncols, rt.nnz) == (gt.nrows, gt.ncols, gt.nnz)
+        for x, y in zip(rt.arrays(), gt.arrays()):
+            assert np.array_equal(x, y), field
