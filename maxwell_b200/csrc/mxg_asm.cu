@@ -6,91 +6,23 @@
 // This translation unit is compiled with -fmad=false: the reference's host code rounds a*b+c twice, and the generated
 // matrices have to carry the very same doubles for the SpMV parity gate to hold downstream.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
 #include "mxasm.h"
 #include "mxg_internal.h"
 #include "mxg_asm_impl.h"
+#include "mxg_scan.cuh"
 #include "mxg_shape.h"
 
 namespace {
 
 constexpr int kAsmBlock = 256;
-constexpr int kScanChunk = 2048;    // items per block of the scan passes (8 per thread)
 
 template <class F>
 __global__ void __launch_bounds__(kAsmBlock) k_asm_rows(int64_t n, F f) {
   for (int64_t i = int64_t(blockIdx.x) * kAsmBlock + threadIdx.x; i < n; i += int64_t(gridDim.x) * kAsmBlock) f(i);
-}
-
-// pass 1: per-chunk totals
-__global__ void __launch_bounds__(kAsmBlock) k_scan_sums(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ sums) {
-  __shared__ int64_t sh[kAsmBlock];
-  const int64_t base = int64_t(blockIdx.x) * kScanChunk;
-  int64_t s = 0;
-  for (int k = 0; k < kScanChunk / kAsmBlock; ++k) {
-    const int64_t i = base + int64_t(k) * kAsmBlock + threadIdx.x;
-    if (i < n) s += in[i];
-  }
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = kAsmBlock / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) sums[blockIdx.x] = sh[0];
-}
-// pass 2: exclusive scan of the chunk totals in one block (a running carry over tiles of kAsmBlock totals)
-__global__ void __launch_bounds__(kAsmBlock) k_scan_chunks(int64_t* __restrict__ sums, int64_t numChunks, int64_t* __restrict__ total) {
-  __shared__ int64_t sh[kAsmBlock];
-  __shared__ int64_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int64_t tile = 0; tile < numChunks; tile += kAsmBlock) {
-    const int64_t i = tile + threadIdx.x;
-    const int64_t v = i < numChunks ? sums[i] : 0;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < kAsmBlock; o <<= 1) {       // inclusive Hillis-Steele
-      const int64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
-    }
-    if (i < numChunks) sums[i] = carry + sh[threadIdx.x] - v;
-    __syncthreads();
-    if (threadIdx.x == kAsmBlock - 1) carry += sh[kAsmBlock - 1];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *total = carry;
-}
-// pass 3: exclusive scan inside every chunk, offset by the chunk's start; thread t owns 8 consecutive items
-__global__ void __launch_bounds__(kAsmBlock) k_scan_write(const int32_t* __restrict__ in, int64_t n, const int64_t* __restrict__ sums,
-                                                          const int64_t* __restrict__ total, int64_t* __restrict__ out) {
-  __shared__ int64_t sh[kAsmBlock];
-  constexpr int per = kScanChunk / kAsmBlock;
-  const int64_t first = int64_t(blockIdx.x) * kScanChunk + int64_t(threadIdx.x) * per;
-  int32_t v[per];
-  int64_t s = 0;
-  for (int k = 0; k < per; ++k) {
-    v[k] = first + k < n ? in[first + k] : 0;
-    s += v[k];
-  }
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 1; o < kAsmBlock; o <<= 1) {
-    const int64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-    __syncthreads();
-    sh[threadIdx.x] += t;
-    __syncthreads();
-  }
-  int64_t run = sums[blockIdx.x] + sh[threadIdx.x] - s;
-  for (int k = 0; k < per; ++k) {
-    if (first + k < n) out[first + k] = run;
-    run += v[k];
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *total;
 }
 
 __global__ void __launch_bounds__(kAsmBlock) k_asm_max(const int32_t* __restrict__ in, int64_t n, int* __restrict__ out) {
@@ -132,16 +64,9 @@ struct DeviceExec {
     check("assembly kernel launch");
   }
   int64_t scan(const int32_t* in, int64_t* out, int64_t n) {
-    const int64_t chunks = std::max<int64_t>((n + kScanChunk - 1) / kScanChunk, 1);
-    int64_t* sums = alloc<int64_t>(chunks + 1);
-    k_scan_sums<<<unsigned(chunks), kAsmBlock, 0, ctx->stream>>>(in, n, sums);
-    k_scan_chunks<<<1, kAsmBlock, 0, ctx->stream>>>(sums, chunks, sums + chunks);
-    k_scan_write<<<unsigned(chunks), kAsmBlock, 0, ctx->stream>>>(in, n, sums, sums + chunks, out);
-    ctx->launches += 3;
-    check("prefix scan launch");
     int64_t total = 0;
-    toHost(&total, sums + chunks, sizeof(int64_t));
-    free(sums);
+    const cudaError_t e = mxg::exclusiveScan(ctx, in, out, n, &total);
+    if (e != cudaSuccess) fail("prefix scan of the operator assembly", e);
     return total;
   }
   int maxOf(const int32_t* in, int64_t n) {
@@ -201,8 +126,9 @@ struct DeviceExec {
 extern "C" {
 
 // MxCrsMatrix::fillComplete for an operator assembled on the device (MxCrsMatrix.cpp:325-342): the rows this rank's
-// row map owns become a device operator (pattern dictionary / sliced ELL, halo plan) without the host ever generating
-// them. The rows pass through the host once, for the layout builder of mxg_crs_create.
+// row map owns become a device operator (pattern dictionary / sliced ELL, halo plan) without the host ever seeing
+// them: the layout is built by kernels too (mxg::crsCreateFromDevice). MXG_LAYOUT_BUILD=host sends the rows through
+// the host layout builder of mxg_crs_create instead (same result; kept for comparison).
 int mxg_crs_create_from_dcsr(mxg_map* row_map, mxg_map* domain_map, const mxg_dcsr* a, int layout, mxg_crs** out) {
   const CsrHandle* A = reinterpret_cast<const CsrHandle*>(a);
   MXG_REQUIRE(row_map && domain_map && A && out, "mxg_crs_create_from_dcsr: NULL argument");
@@ -226,6 +152,24 @@ int mxg_crs_create_from_dcsr(mxg_map* row_map, mxg_map* domain_map, const mxg_dc
                   "mxg_crs_create_from_dcsr: the row map is not a contiguous run of the simulation's %s map",
                   rf == mxy::FIELD_B ? "B" : (rf == mxy::FIELD_E ? "E" : "psi"));
     }
+    // this rank's columns: the run of the column field map its domain map owns
+    int64_t c0 = 0;
+    bool domIsRun = true;
+    if (domain_map->nLocal > 0) {
+      c0 = int64_t(std::lower_bound(colG.begin(), colG.end(), domain_map->gids.front()) - colG.begin());
+      domIsRun = c0 + domain_map->nLocal <= int64_t(colG.size()) &&
+                 std::memcmp(colG.data() + c0, domain_map->gids.data(), size_t(domain_map->nLocal) * sizeof(int64_t)) == 0;
+    }
+    const char* how = std::getenv("MXG_LAYOUT_BUILD");
+    const bool onDevice = !(how && std::strcmp(how, "host") == 0) && domIsRun && row_map->perm.empty() && domain_map->perm.empty();
+    if (onDevice) {
+      // layout built on the device (mxg_spmv.cu: hash-table pattern dictionary, sliced ELL, inverse diagonal as kernels)
+      const int64_t* rp = (A->isComplex ? A->c.rowptr : A->r.rowptr) + r0;
+      const int32_t* col = A->isComplex ? A->c.col : A->r.col;
+      const void* val = A->isComplex ? static_cast<const void*>(A->c.val) : static_cast<const void*>(A->r.val);
+      return mxg::crsCreateFromDevice(row_map, domain_map, rp, col, val, c0, int64_t(colG.size()), colG.data(), A->isComplex, layout, out);
+    }
+    // MXG_LAYOUT_BUILD=host (or maps the device builder does not take): the rows pass through the host layout builder
     const int64_t n = r1 - r0;
     std::vector<int64_t> rowptr(static_cast<size_t>(n) + 1, 0);
     int rc = mxg_dcsr_download(a, r0, r1, rowptr.data(), nullptr, nullptr);

@@ -27,6 +27,7 @@
 #include "mxg_ilv_model.h"
 #include "mxg_order.h"
 #include "mxg_spmm_win.cuh"
+#include "mxg_scan.cuh"
 
 using namespace mxg;
 
@@ -546,7 +547,7 @@ int launchBoundary(const mxg_crs* A, const XSource<T>& X, const ColTable<T>& Y, 
   return launchSegments<T, true>(A, b, e, X, Y, nvec, ep, st, W);
 }
 
-inline uint64_t mix64(uint64_t h, uint64_t v) {
+__host__ __device__ inline uint64_t mix64(uint64_t h, uint64_t v) {
   h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
   h *= 0xBF58476D1CE4E5B9ull;
   return h ^ (h >> 29);
@@ -1137,6 +1138,69 @@ int planHalo(mxg_crs* A, const std::vector<int64_t>& ghosts, const std::vector<i
   return setupP2P(A, int64_t(ghosts.size()));
 }
 
+// Kernel plans that depend on the row -> pattern map: thread -> row interleave of the gather kernels and the x windows of
+// the windowed kernel. Shared by the host layout builder and the device one (which hands in a host copy of rowPat).
+template <class T>
+int planKernels(mxg_crs* A, const std::vector<int32_t>& rowPat, const std::vector<int32_t>& patOff, const std::vector<PatEntry<T>>& pat) {
+  mxg_ctx* ctx = A->ctx;
+  const int64_t nRows = A->nRows, nLoc = A->nLoc;
+  int rc = MXG_OK;
+  // ---- thread -> row assignment of the dictionary kernel: plain, or stride-3 component interleave. Chosen by a
+  // line-count model over sampled interior tiles (mxg_ilv_model.h, with the B200 measurements that calibrate it).
+  // MXG_SPMV_ILV = 1 / 3 forces either.
+  {
+    const char* env = std::getenv("MXG_SPMV_ILV");
+    const std::string mode = env ? env : "auto";
+    A->ilv = 1;
+    if (mode == "3") A->ilv = 3;
+    else if (mode != "1" && A->dictRows > 0) {
+      const PatEntry<T>* pe = pat.data();
+      const mxg::IlvCost cost = mxg::ilvCostModel(rowPat.data(), patOff.data(), [pe](int32_t q) { return pe[q].d; }, A->intBegin,
+                                                  A->intEnd, int(sizeof(T)), int(sizeof(PatEntry<T>)));
+      if (mxg::ilvWins(cost)) A->ilv = 3;
+    }
+  }
+
+  // ---- windowed dictionary kernel: per-tile x windows (mxg_spmm_win.cuh). MXG_SPMV_WIN=0 keeps the gather kernels.
+  {
+    const char* env = std::getenv("MXG_SPMV_WIN");
+    const bool want = !(env && std::strcmp(env, "0") == 0);
+    if (want && A->dictRows > 0 && nLoc + A->gLo + A->gHi < (int64_t(1) << 30)) {
+      constexpr int R = kWinThreads * WinCfg<T>::RPT;
+      constexpr int align = 16 / int(sizeof(T)) > 0 ? 16 / int(sizeof(T)) : 1;
+      const PatEntry<T>* pe = pat.data();
+      int64_t maxTotal = 0, valid = 0;
+      std::vector<WinTile> tiles = planWinTiles(rowPat.data(), patOff.data(), A->numPats, [pe](int32_t q) { return int64_t(pe[q].d); }, nRows,
+                                                nLoc, R, align, int64_t(std::min(kWinBufBudget, kWinSmemMax - winSmemHeader<T>()) / sizeof(T)), &maxTotal, &valid);
+      if (valid > 0) {
+        WinTile* dT = nullptr;
+        if ((rc = uploadVec(tiles, &dT, &A->deviceBytes, ctx))) return rc;
+        A->dWinTiles = dT;
+        A->winR = R;
+        A->winTiles = int64_t(tiles.size());
+        A->winValid = valid;
+        A->winBufElems = maxTotal;
+        A->winMaxVec = 1;
+        if (const char* mv = std::getenv("MXG_WIN_MAXVEC")) A->winMaxVec = std::atoi(mv);
+        // thread -> row assignment: component triples (GID = comp + 3 cell) share patterns at distance 3, scalar fields at 1
+        int64_t same1 = 0, same3 = 0;
+        for (int64_t r = 0; r + 3 < nRows; ++r) {
+          if (rowPat[r] < 0) continue;
+          same1 += rowPat[r] == rowPat[r + 1];
+          same3 += rowPat[r] == rowPat[r + 3];
+        }
+        A->winIlv = same3 > same1 ? 3 : 1;
+        if (const char* iv = std::getenv("MXG_SPMV_ILV")) {
+          if (std::strcmp(iv, "1") == 0) A->winIlv = 1;
+          if (std::strcmp(iv, "3") == 0) A->winIlv = 3;
+        }
+      }
+    }
+  }
+
+  return rc;
+}
+
 template <class T>
 int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const double* valsIn, int layout) {
   mxg_ctx* ctx = A->ctx;
@@ -1313,58 +1377,7 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
   // pillbox-256 -- a warp holds ~3 different patterns and divergent LDC replays cost more than L1 broadcast loads;
   // the 16 KB parameter block also lengthened every launch. profiles/README_r01.md.)
 
-  // ---- thread -> row assignment of the dictionary kernel: plain, or stride-3 component interleave. Chosen by a
-  // line-count model over sampled interior tiles (mxg_ilv_model.h, with the B200 measurements that calibrate it).
-  // MXG_SPMV_ILV = 1 / 3 forces either.
-  {
-    const char* env = std::getenv("MXG_SPMV_ILV");
-    const std::string mode = env ? env : "auto";
-    A->ilv = 1;
-    if (mode == "3") A->ilv = 3;
-    else if (mode != "1" && A->dictRows > 0) {
-      const PatEntry<T>* pe = pat.data();
-      const mxg::IlvCost cost = mxg::ilvCostModel(rowPat.data(), patOff.data(), [pe](int32_t q) { return pe[q].d; }, A->intBegin,
-                                                  A->intEnd, int(sizeof(T)), int(sizeof(PatEntry<T>)));
-      if (mxg::ilvWins(cost)) A->ilv = 3;
-    }
-  }
-
-  // ---- windowed dictionary kernel: per-tile x windows (mxg_spmm_win.cuh). MXG_SPMV_WIN=0 keeps the gather kernels.
-  {
-    const char* env = std::getenv("MXG_SPMV_WIN");
-    const bool want = !(env && std::strcmp(env, "0") == 0);
-    if (want && A->dictRows > 0 && nLoc + A->gLo + A->gHi < (int64_t(1) << 30)) {
-      constexpr int R = kWinThreads * WinCfg<T>::RPT;
-      constexpr int align = 16 / int(sizeof(T)) > 0 ? 16 / int(sizeof(T)) : 1;
-      const PatEntry<T>* pe = pat.data();
-      int64_t maxTotal = 0, valid = 0;
-      std::vector<WinTile> tiles = planWinTiles(rowPat.data(), patOff.data(), A->numPats, [pe](int32_t q) { return int64_t(pe[q].d); }, nRows,
-                                                nLoc, R, align, int64_t(std::min(kWinBufBudget, kWinSmemMax - winSmemHeader<T>()) / sizeof(T)), &maxTotal, &valid);
-      if (valid > 0) {
-        WinTile* dT = nullptr;
-        if ((rc = uploadVec(tiles, &dT, &A->deviceBytes, ctx))) return rc;
-        A->dWinTiles = dT;
-        A->winR = R;
-        A->winTiles = int64_t(tiles.size());
-        A->winValid = valid;
-        A->winBufElems = maxTotal;
-        A->winMaxVec = 1;
-        if (const char* mv = std::getenv("MXG_WIN_MAXVEC")) A->winMaxVec = std::atoi(mv);
-        // thread -> row assignment: component triples (GID = comp + 3 cell) share patterns at distance 3, scalar fields at 1
-        int64_t same1 = 0, same3 = 0;
-        for (int64_t r = 0; r + 3 < nRows; ++r) {
-          if (rowPat[r] < 0) continue;
-          same1 += rowPat[r] == rowPat[r + 1];
-          same3 += rowPat[r] == rowPat[r + 3];
-        }
-        A->winIlv = same3 > same1 ? 3 : 1;
-        if (const char* iv = std::getenv("MXG_SPMV_ILV")) {
-          if (std::strcmp(iv, "1") == 0) A->winIlv = 1;
-          if (std::strcmp(iv, "3") == 0) A->winIlv = 3;
-        }
-      }
-    }
-  }
+  if ((rc = planKernels<T>(A, rowPat, patOff, pat))) return rc;
 
   // ---- general rows in sliced ELL; the three row classes (leading boundary, interior,
   // trailing boundary) each start on a slice boundary so they can be launched separately
@@ -1451,7 +1464,490 @@ int buildImpl(mxg_crs* A, const int64_t* rowptr, const int64_t* colGids, const d
   return MXG_OK;
 }
 
+
+// ---- layout built on the device ---------------------------------------------------------------------------------------
+// The same layout as buildImpl, for an operator whose CRS rows already sit in device memory (the operator assembly,
+// mxg_asm.cu): ghost discovery, extended column indices, the pattern dictionary (a device hash table instead of the host
+// unordered_map), sliced ELL and the inverse diagonal are kernels; the host keeps what is small or collective -- pattern
+// ordering (a few thousand candidates), the halo plan and the tile planner on a downloaded row -> pattern map.
+struct Scratch {
+  std::vector<void*> p;
+  ~Scratch() { for (void* q : p) if (q) cudaFree(q); }
+  template <class U>
+  U* get(int64_t n) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, size_t(n > 0 ? n : 1) * sizeof(U)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    p.push_back(q);
+    return static_cast<U*>(q);
+  }
+};
+
+constexpr unsigned long long kLbEmpty = 0xFFFFFFFFFFFFFFFFull;
+
+__global__ void k_lb_mark_ghosts(const int32_t* __restrict__ col, int64_t cnt, int64_t c0, int64_t c1, int32_t* __restrict__ flag) {
+  for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < cnt; q += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t l = col[q];
+    if (l < c0 || l >= c1) flag[l] = 1;
+  }
+}
+__global__ void k_lb_compact(const int32_t* __restrict__ flag, const int64_t* __restrict__ off, int64_t n, int32_t* __restrict__ list) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    if (flag[i]) list[off[i]] = int32_t(i);
+}
+// extended local column of every entry (owned: 0 .. nLoc-1; ghosts below / above the owned range: negative / >= nLoc)
+__global__ void k_lb_ext(const int64_t* __restrict__ rp, const int32_t* __restrict__ colG, int64_t nRows, int64_t base, int64_t c0,
+                         int64_t c1, int64_t nLoc, int64_t gLo, const int64_t* __restrict__ ghostOff, int32_t* __restrict__ ext,
+                         uint8_t* __restrict__ needs, int* __restrict__ err) {
+  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < nRows; r += int64_t(gridDim.x) * blockDim.x) {
+    bool ghost = false;
+    for (int64_t q = rp[r]; q < rp[r + 1]; ++q) {
+      const int64_t l = colG[q];
+      int32_t e;
+      if (l >= c0 && l < c1) e = int32_t(l - c0);
+      else if (ghostOff) {
+        const int64_t pos = ghostOff[l];
+        e = pos < gLo ? int32_t(pos - gLo) : int32_t(nLoc + (pos - gLo));
+        ghost = true;
+      } else { *err = 1; e = 0; }
+      ext[q - base] = e;
+    }
+    if (needs) needs[r] = ghost ? 1 : 0;
+  }
+}
+
+template <class T>
+__device__ __forceinline__ uint64_t lbRowHash(const int64_t* rp, const int32_t* ext, const T* valG, int64_t base, int64_t r) {
+  constexpr int w = sizeof(T) / sizeof(double);
+  const int64_t b = rp[r], e = rp[r + 1];
+  uint64_t h = mix64(0x1234567ull, uint64_t(e - b));
+  for (int64_t q = b; q < e; ++q) {
+    h = mix64(h, uint64_t(int64_t(ext[q - base]) - r));
+    const uint64_t* bits = reinterpret_cast<const uint64_t*>(valG + q);
+    for (int t = 0; t < w; ++t) h = mix64(h, bits[t]);
+  }
+  return h == kLbEmpty ? h ^ 1ull : h;
+}
+template <class T>
+__device__ __forceinline__ bool lbSameRow(const int64_t* rp, const int32_t* ext, const T* valG, int64_t base, int64_t a, int64_t b) {
+  constexpr int w = sizeof(T) / sizeof(double);
+  const int64_t la = rp[a + 1] - rp[a];
+  if (la != rp[b + 1] - rp[b]) return false;
+  for (int64_t k = 0; k < la; ++k) {
+    const int64_t qa = rp[a] + k, qb = rp[b] + k;
+    if (int64_t(ext[qa - base]) - a != int64_t(ext[qb - base]) - b) return false;
+    const uint64_t* va = reinterpret_cast<const uint64_t*>(valG + qa);
+    const uint64_t* vb = reinterpret_cast<const uint64_t*>(valG + qb);
+    for (int t = 0; t < w; ++t)
+      if (va[t] != vb[t]) return false;
+  }
+  return true;
+}
+// rows -> hash-table slots (open addressing, linear probing); the representative of a slot is its first row
+template <class T>
+__global__ void k_lb_hash_insert(const int64_t* __restrict__ rp, const int32_t* __restrict__ ext, const T* __restrict__ valG, int64_t base,
+                                 int64_t nRows, unsigned long long* __restrict__ keys, int32_t* __restrict__ rep, int32_t* __restrict__ count,
+                                 int32_t* __restrict__ rowSlot, uint64_t mask) {
+  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < nRows; r += int64_t(gridDim.x) * blockDim.x) {
+    if (rp[r + 1] == rp[r]) { rowSlot[r] = -1; continue; }        // empty rows go to the general path (y = 0)
+    const unsigned long long h = lbRowHash<T>(rp, ext, valG, base, r);
+    uint64_t slot = (h * 0x9E3779B97F4A7C15ull >> 20) & mask;
+    for (;;) {
+      const unsigned long long old = atomicCAS(keys + slot, kLbEmpty, h);
+      if (old == kLbEmpty || old == h) break;
+      slot = (slot + 1) & mask;
+    }
+    atomicMin(rep + slot, int32_t(r));
+    atomicAdd(count + slot, 1);
+    rowSlot[r] = int32_t(slot);
+  }
+}
+// a 64-bit collision (different rows, same hash) sends the later row to the general path
+template <class T>
+__global__ void k_lb_verify(const int64_t* __restrict__ rp, const int32_t* __restrict__ ext, const T* __restrict__ valG, int64_t base,
+                            int64_t nRows, const int32_t* __restrict__ rep, int32_t* __restrict__ count, int32_t* __restrict__ rowSlot) {
+  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < nRows; r += int64_t(gridDim.x) * blockDim.x) {
+    const int32_t s = rowSlot[r];
+    if (s < 0) continue;
+    const int64_t lead = rep[s];
+    if (lead != r && !lbSameRow<T>(rp, ext, valG, base, lead, r)) {
+      rowSlot[r] = -1;
+      atomicSub(count + s, 1);
+    }
+  }
+}
+__global__ void k_lb_occupied(const unsigned long long* __restrict__ keys, int64_t n, int32_t* __restrict__ flag) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    flag[i] = keys[i] != kLbEmpty ? 1 : 0;
+}
+__global__ void k_lb_cands(const int32_t* __restrict__ flag, const int64_t* __restrict__ off, int64_t n, const int32_t* __restrict__ rep,
+                           const int32_t* __restrict__ count, const int64_t* __restrict__ rp, int32_t* __restrict__ candRep,
+                           int32_t* __restrict__ candCount, int32_t* __restrict__ candLen) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    if (flag[i]) {
+      const int64_t c = off[i];
+      const int32_t r = rep[i];
+      candRep[c] = r;
+      candCount[c] = count[i];
+      candLen[c] = int32_t(rp[r + 1] - rp[r]);
+    }
+}
+__global__ void k_lb_row_pat(const int32_t* __restrict__ rowSlot, const int64_t* __restrict__ off, const int32_t* __restrict__ candPat,
+                             int64_t nRows, int32_t* __restrict__ rowPat) {
+  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < nRows; r += int64_t(gridDim.x) * blockDim.x) {
+    const int32_t s = rowSlot[r];
+    rowPat[r] = s >= 0 ? candPat[off[s]] : -1;
+  }
+}
+__device__ __forceinline__ void lbStoreEntry(PatEntry<double>* e, double v, int32_t d) { e->v = v; e->d = d; e->pad = 0; }
+__device__ __forceinline__ void lbStoreEntry(PatEntry<zd>* e, zd v, int32_t d) {
+  e->vx = v.x; e->vy = v.y; e->d = d; e->pad[0] = e->pad[1] = e->pad[2] = 0;
+}
+template <class T>
+__global__ void k_lb_fill_pat(int64_t numPats, const int32_t* __restrict__ patRep, const int32_t* __restrict__ patOff,
+                              const int64_t* __restrict__ rp, const int32_t* __restrict__ ext, const T* __restrict__ valG, int64_t base,
+                              PatEntry<T>* __restrict__ pat) {
+  for (int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; p < numPats; p += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = patRep[p];
+    const int64_t b = rp[r], n = rp[r + 1] - b;
+    for (int64_t k = 0; k < n; ++k) lbStoreEntry(pat + patOff[p] + k, valG[b + k], int32_t(int64_t(ext[b + k - base]) - r));
+  }
+}
+__global__ void k_lb_is_gen(const int32_t* __restrict__ rowPat, int64_t nRows, int32_t* __restrict__ flag) {
+  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < nRows; r += int64_t(gridDim.x) * blockDim.x)
+    flag[r] = rowPat[r] < 0 ? 1 : 0;
+}
+// general rows in three classes (leading boundary, interior, trailing boundary), each padded to whole slices
+__global__ void k_lb_gen_rows(const int32_t* __restrict__ flag, const int64_t* __restrict__ off, const int64_t* __restrict__ rp, int64_t nRows,
+                              int64_t intBegin, int64_t intEnd, int64_t off0, int64_t off1, int64_t base1, int64_t base2,
+                              int32_t* __restrict__ genRow, int32_t* __restrict__ genLen) {
+  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < nRows; r += int64_t(gridDim.x) * blockDim.x) {
+    if (!flag[r]) continue;
+    int64_t pos;
+    if (r < intBegin) pos = off[r];
+    else if (r < intEnd) pos = base1 + (off[r] - off0);
+    else pos = base2 + (off[r] - off1);
+    genRow[pos] = int32_t(r);
+    genLen[pos] = int32_t(rp[r + 1] - rp[r]);
+  }
+}
+__global__ void k_lb_slice_width(const int32_t* __restrict__ genLen, int64_t nSlices, int32_t* __restrict__ w) {
+  for (int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; s < nSlices; s += int64_t(gridDim.x) * blockDim.x) {
+    int32_t m = 0;
+    for (int l = 0; l < 32; ++l) m = max(m, genLen[s * 32 + l]);
+    w[s] = m;
+  }
+}
+__global__ void k_lb_times32(int64_t* __restrict__ p, int64_t n) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) p[i] *= 32;
+}
+// one warp per slice: lane l owns row l of the slice; padding entries point at a column a real entry of the slice uses
+// (value 0), so the kernel may load through them unconditionally
+template <class T>
+__global__ void k_lb_fill_ell(const int32_t* __restrict__ genRow, const int32_t* __restrict__ genLen, const int64_t* __restrict__ slicePtr,
+                              const int64_t* __restrict__ rp, const int32_t* __restrict__ ext, const T* __restrict__ valG, int64_t base,
+                              int64_t nSlices, int32_t* __restrict__ ellCol, T* __restrict__ ellVal) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nWarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t s = warp; s < nSlices; s += nWarps) {
+    const int64_t i = s * 32 + lane;
+    const int64_t row = genRow[i];
+    const int32_t len = genLen[i];
+    const int64_t b = row >= 0 ? rp[row] : 0;
+    const bool real = row >= 0 && len > 0;
+    const unsigned have = __ballot_sync(0xffffffffu, real);
+    int32_t fallback = real ? ext[b - base] : 0;
+    fallback = have ? __shfl_sync(0xffffffffu, fallback, __ffs(have) - 1) : 0;
+    const int64_t p0 = slicePtr[s];
+    const int32_t width = int32_t((slicePtr[s + 1] - p0) >> 5);
+    for (int32_t k = 0; k < width; ++k) {
+      const bool on = row >= 0 && k < len;
+      ellCol[p0 + int64_t(k) * 32 + lane] = on ? ext[b + k - base] : fallback;
+      ellVal[p0 + int64_t(k) * 32 + lane] = on ? valG[b + k] : zeroOf<T>();
+    }
+  }
+}
+__device__ __forceinline__ double lbInverse(double d) { return 1.0 / d; }
+__device__ __forceinline__ zd lbInverse(zd d) {
+  const double m2 = __dadd_rn(__dmul_rn(d.x, d.x), __dmul_rn(d.y, d.y));    // two roundings, like the host builder
+  return {d.x / m2, -d.y / m2};
+}
+template <class T>
+__global__ void k_lb_inv_diag(const int64_t* __restrict__ rp, const int32_t* __restrict__ ext, const T* __restrict__ valG, int64_t base,
+                              int64_t nRows, T* __restrict__ inv) {
+  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < nRows; r += int64_t(gridDim.x) * blockDim.x) {
+    T out = zeroOf<T>();
+    for (int64_t q = rp[r]; q < rp[r + 1]; ++q)
+      if (ext[q - base] == r) {
+        const T d = valG[q];
+        out = isZero(d) ? zeroOf<T>() : lbInverse(d);      // the last matching entry wins, as in buildImpl (rows are merged: one)
+      }
+    inv[r] = out;
+  }
+}
+
+inline unsigned lbGrid(int64_t n, int block = 256) {
+  const int64_t b = (n + block - 1) / block;
+  return unsigned(std::max<int64_t>(1, std::min<int64_t>(b, int64_t(1) << 20)));
+}
+#define MXG_LB_ALLOC(var, type, count)                                                          \
+  type* var = tmp.get<type>(count);                                                             \
+  MXG_REQUIRE(var != nullptr, "mxg_crs_create_from_dcsr: out of device memory (%s)", #var)
+#define MXG_LB_KEEP(dst, type, count)                                                           \
+  do {                                                                                          \
+    void* q_ = nullptr;                                                                         \
+    MXG_CUDA(cudaMalloc(&q_, size_t((count) > 0 ? (count) : 1) * sizeof(type)));                \
+    dst = static_cast<type*>(q_);                                                               \
+    A->deviceBytes += size_t((count) > 0 ? (count) : 1) * sizeof(type);                         \
+  } while (0)
+
+template <class T>
+int buildFromDeviceImpl(mxg_crs* A, const int64_t* dRp, const int32_t* dColG, const void* dValRaw, int64_t c0, int64_t colFieldSize,
+                        const int64_t* colFieldGids, int layout) {
+  mxg_ctx* ctx = A->ctx;
+  cudaStream_t st = ctx->stream;
+  const T* dValG = static_cast<const T*>(dValRaw);
+  const int64_t nRows = A->nRows, nLoc = A->nLoc, c1 = c0 + nLoc;
+  const mxg_map* dom = A->domMap;
+  MXG_REQUIRE(dom->nGlobal < (int64_t(1) << 31), "mxg_crs_create: global size must fit in 31 bits");
+  Scratch tmp;
+  int64_t ends[2] = {0, 0};
+  MXG_CUDA(cudaMemcpyAsync(&ends[0], dRp, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  MXG_CUDA(cudaMemcpyAsync(&ends[1], dRp + nRows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  MXG_CUDA(cudaStreamSynchronize(st));
+  const int64_t base = ends[0], cnt = ends[1] - ends[0];
+  A->nnz = cnt;
+  const int64_t domLo = nLoc ? dom->gids.front() : 0, domHi = nLoc ? dom->gids.back() : -1;
+
+  // ---- ghosts: referenced columns outside this rank's run of the column field map
+  std::vector<int64_t> ghosts;
+  int64_t* dGhostOff = nullptr;
+  if (ctx->nranks > 1) {
+    MXG_LB_ALLOC(dFlag, int32_t, colFieldSize);
+    MXG_LB_ALLOC(dOff, int64_t, colFieldSize + 1);
+    MXG_CUDA(cudaMemsetAsync(dFlag, 0, size_t(colFieldSize) * sizeof(int32_t), st));
+    if (cnt > 0) k_lb_mark_ghosts<<<lbGrid(cnt), 256, 0, st>>>(dColG + base, cnt, c0, c1, dFlag);
+    int64_t ng = 0;
+    MXG_CUDA(exclusiveScan(ctx, dFlag, dOff, colFieldSize, &ng));
+    if (ng > 0) {
+      MXG_LB_ALLOC(dList, int32_t, ng);
+      k_lb_compact<<<lbGrid(colFieldSize), 256, 0, st>>>(dFlag, dOff, colFieldSize, dList);
+      std::vector<int32_t> list(static_cast<size_t>(ng), 0);
+      MXG_CUDA(cudaMemcpyAsync(list.data(), dList, size_t(ng) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      MXG_CUDA(cudaStreamSynchronize(st));
+      ghosts.resize(static_cast<size_t>(ng));
+      for (int64_t i = 0; i < ng; ++i) ghosts[size_t(i)] = colFieldGids[list[size_t(i)]];   // ascending: the field map is
+    }
+    dGhostOff = dOff;
+    ctx->launches += 2;
+  }
+  A->gLo = int64_t(std::lower_bound(ghosts.begin(), ghosts.end(), domLo) - ghosts.begin());
+  if (nLoc == 0) A->gLo = 0;
+  A->gHi = int64_t(ghosts.size()) - A->gLo;
+  {
+    std::vector<int32_t> lookup;
+    if (ctx->nranks > 1) {
+      lookup.assign(size_t(dom->nGlobal), -1);
+      for (int64_t i = 0; i < nLoc; ++i) lookup[size_t(dom->gids[size_t(i)])] = int32_t(i);
+    }
+    const int rcH = planHalo(A, ghosts, lookup, domLo, domHi);
+    if (rcH) return rcH;
+  }
+
+  // ---- extended local columns, rows that need ghost values
+  MXG_LB_ALLOC(dExt, int32_t, cnt);
+  MXG_LB_ALLOC(dErr, int, 1);
+  uint8_t* dNeeds = nullptr;
+  if (ctx->nranks > 1) { MXG_LB_ALLOC(needs_, uint8_t, nRows); dNeeds = needs_; }
+  MXG_CUDA(cudaMemsetAsync(dErr, 0, sizeof(int), st));
+  if (nRows > 0) k_lb_ext<<<lbGrid(nRows), 256, 0, st>>>(dRp, dColG, nRows, base, c0, c1, nLoc, A->gLo, dGhostOff, dExt, dNeeds, dErr);
+  ctx->launches++;
+  int hErr = 0;
+  MXG_CUDA(cudaMemcpyAsync(&hErr, dErr, sizeof(int), cudaMemcpyDeviceToHost, st));
+  std::vector<uint8_t> needs;
+  if (dNeeds) {
+    needs.resize(static_cast<size_t>(nRows));
+    MXG_CUDA(cudaMemcpyAsync(needs.data(), dNeeds, size_t(nRows), cudaMemcpyDeviceToHost, st));
+  }
+  MXG_CUDA(cudaStreamSynchronize(st));
+  MXG_REQUIRE(hErr == 0, "mxg_crs_create: a column is not in the domain map (single-rank context)");
+  A->intBegin = 0;
+  A->intEnd = nRows;
+  if (dNeeds) {       // interior range = longest run of rows without ghost needs
+    int64_t bestB = 0, bestE = 0, runB = 0;
+    for (int64_t r = 0; r <= nRows; ++r)
+      if (r == nRows || needs[size_t(r)]) {
+        if (r - runB > bestE - bestB) { bestB = runB; bestE = r; }
+        runB = r + 1;
+      }
+    A->intBegin = bestB;
+    A->intEnd = bestE;
+    for (int64_t r = 0; r < nRows; ++r) A->ghostRows += needs[size_t(r)];
+  }
+
+  // ---- pattern dictionary
+  std::vector<int32_t> rowPat(static_cast<size_t>(nRows), -1), patOff(1, 0);
+  std::vector<PatEntry<T>> pat;
+  MXG_LB_KEEP(A->dRowPat, int32_t, nRows);
+  const bool sameMaps = A->rowMap == A->domMap || A->rowMap->gids == A->domMap->gids;
+  bool haveDict = false;
+  if (layout != 1 && sameMaps && nRows > 0) {
+    int64_t tableSize = 1024;
+    while (tableSize < 2 * nRows) tableSize <<= 1;
+    MXG_LB_ALLOC(dKeys, unsigned long long, tableSize);
+    MXG_LB_ALLOC(dRep, int32_t, tableSize);
+    MXG_LB_ALLOC(dCount, int32_t, tableSize);
+    MXG_LB_ALLOC(dRowSlot, int32_t, nRows);
+    MXG_CUDA(cudaMemsetAsync(dKeys, 0xFF, size_t(tableSize) * sizeof(unsigned long long), st));
+    MXG_CUDA(cudaMemsetAsync(dRep, 0x7F, size_t(tableSize) * sizeof(int32_t), st));
+    MXG_CUDA(cudaMemsetAsync(dCount, 0, size_t(tableSize) * sizeof(int32_t), st));
+    k_lb_hash_insert<T><<<lbGrid(nRows), 256, 0, st>>>(dRp, dExt, dValG, base, nRows, dKeys, dRep, dCount, dRowSlot, uint64_t(tableSize - 1));
+    k_lb_verify<T><<<lbGrid(nRows), 256, 0, st>>>(dRp, dExt, dValG, base, nRows, dRep, dCount, dRowSlot);
+    MXG_LB_ALLOC(dOcc, int32_t, tableSize);
+    MXG_LB_ALLOC(dSlotOff, int64_t, tableSize + 1);
+    k_lb_occupied<<<lbGrid(tableSize), 256, 0, st>>>(dKeys, tableSize, dOcc);
+    int64_t nCand = 0;
+    MXG_CUDA(exclusiveScan(ctx, dOcc, dSlotOff, tableSize, &nCand));
+    ctx->launches += 3;
+    MXG_LB_ALLOC(dCandRep, int32_t, nCand);
+    MXG_LB_ALLOC(dCandCount, int32_t, nCand);
+    MXG_LB_ALLOC(dCandLen, int32_t, nCand);
+    MXG_LB_ALLOC(dCandPat, int32_t, nCand);
+    k_lb_cands<<<lbGrid(tableSize), 256, 0, st>>>(dOcc, dSlotOff, tableSize, dRep, dCount, dRp, dCandRep, dCandCount, dCandLen);
+    std::vector<int32_t> candRep(static_cast<size_t>(nCand), 0), candCount(static_cast<size_t>(nCand), 0), candLen(static_cast<size_t>(nCand), 0);
+    MXG_CUDA(cudaMemcpyAsync(candRep.data(), dCandRep, size_t(nCand) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MXG_CUDA(cudaMemcpyAsync(candCount.data(), dCandCount, size_t(nCand) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MXG_CUDA(cudaMemcpyAsync(candLen.data(), dCandLen, size_t(nCand) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MXG_CUDA(cudaStreamSynchronize(st));
+    // pattern numbering as in buildImpl: candidates in order of first appearance, most frequent first (stable), at least 4 rows
+    std::vector<int32_t> byRow(static_cast<size_t>(nCand), 0);
+    for (int64_t c = 0; c < nCand; ++c) byRow[size_t(c)] = int32_t(c);
+    std::sort(byRow.begin(), byRow.end(), [&](int32_t a, int32_t b) { return candRep[size_t(a)] < candRep[size_t(b)]; });
+    std::stable_sort(byRow.begin(), byRow.end(), [&](int32_t a, int32_t b) { return candCount[size_t(a)] > candCount[size_t(b)]; });
+    const int minCount = 4;
+    std::vector<int32_t> candPat(static_cast<size_t>(nCand), -1), patRep;
+    for (int32_t c : byRow) {
+      if (candCount[size_t(c)] < minCount) continue;
+      candPat[size_t(c)] = int32_t(patRep.size());
+      patRep.push_back(candRep[size_t(c)]);
+      patOff.push_back(patOff.back() + candLen[size_t(c)]);
+      A->dictRows += candCount[size_t(c)];
+    }
+    A->numPats = int64_t(patRep.size());
+    A->patEntries = patOff.back();
+    MXG_CUDA(cudaMemcpyAsync(dCandPat, candPat.data(), size_t(nCand) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    k_lb_row_pat<<<lbGrid(nRows), 256, 0, st>>>(dRowSlot, dSlotOff, dCandPat, nRows, A->dRowPat);
+    MXG_LB_ALLOC(dPatRep, int32_t, A->numPats);
+    MXG_LB_KEEP(A->dPatOff, int32_t, A->numPats + 1);
+    PatEntry<T>* dPat = nullptr;
+    MXG_LB_KEEP(dPat, PatEntry<T>, A->patEntries);
+    A->dPat = dPat;
+    MXG_CUDA(cudaMemcpyAsync(dPatRep, patRep.data(), patRep.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    MXG_CUDA(cudaMemcpyAsync(A->dPatOff, patOff.data(), patOff.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (A->numPats > 0) k_lb_fill_pat<T><<<lbGrid(A->numPats, 64), 64, 0, st>>>(A->numPats, dPatRep, A->dPatOff, dRp, dExt, dValG, base, dPat);
+    ctx->launches += 3;
+    pat.resize(static_cast<size_t>(A->patEntries));
+    MXG_CUDA(cudaMemcpyAsync(rowPat.data(), A->dRowPat, size_t(nRows) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (A->patEntries > 0) MXG_CUDA(cudaMemcpyAsync(pat.data(), dPat, size_t(A->patEntries) * sizeof(PatEntry<T>), cudaMemcpyDeviceToHost, st));
+    MXG_CUDA(cudaStreamSynchronize(st));      // candPat / patRep / patOff are host temporaries: done with them here
+    haveDict = true;
+  }
+  if (!haveDict) {
+    MXG_CUDA(cudaMemsetAsync(A->dRowPat, 0xFF, size_t(std::max<int64_t>(nRows, 1)) * sizeof(int32_t), st));
+    MXG_LB_KEEP(A->dPatOff, int32_t, 1);
+    MXG_CUDA(cudaMemsetAsync(A->dPatOff, 0, sizeof(int32_t), st));
+    PatEntry<T>* dPat = nullptr;
+    MXG_LB_KEEP(dPat, PatEntry<T>, 1);
+    A->dPat = dPat;
+  }
+  int rc = planKernels<T>(A, rowPat, patOff, pat);
+  if (rc) return rc;
+
+  // ---- general rows in sliced ELL
+  MXG_LB_ALLOC(dIsGen, int32_t, nRows);
+  MXG_LB_ALLOC(dGenOff, int64_t, nRows + 1);
+  if (nRows > 0) k_lb_is_gen<<<lbGrid(nRows), 256, 0, st>>>(A->dRowPat, nRows, dIsGen);
+  int64_t totalGen = 0;
+  MXG_CUDA(exclusiveScan(ctx, dIsGen, dGenOff, nRows, &totalGen));
+  int64_t offs[2] = {0, totalGen};
+  MXG_CUDA(cudaMemcpyAsync(&offs[0], dGenOff + A->intBegin, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  MXG_CUDA(cudaMemcpyAsync(&offs[1], dGenOff + A->intEnd, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  MXG_CUDA(cudaStreamSynchronize(st));
+  auto pad32 = [](int64_t v) { return (v + 31) / 32 * 32; };
+  const int64_t n0 = offs[0], n1 = offs[1] - offs[0], n2 = totalGen - offs[1];
+  A->genIntBegin = pad32(n0);
+  A->genIntEnd = A->genIntBegin + pad32(n1);
+  A->nGen = A->genIntEnd + pad32(n2);
+  MXG_LB_KEEP(A->dGenRow, int32_t, A->nGen);
+  MXG_LB_KEEP(A->dGenLen, int32_t, A->nGen);
+  MXG_CUDA(cudaMemsetAsync(A->dGenRow, 0xFF, size_t(std::max<int64_t>(A->nGen, 1)) * sizeof(int32_t), st));
+  MXG_CUDA(cudaMemsetAsync(A->dGenLen, 0, size_t(std::max<int64_t>(A->nGen, 1)) * sizeof(int32_t), st));
+  if (nRows > 0)
+    k_lb_gen_rows<<<lbGrid(nRows), 256, 0, st>>>(dIsGen, dGenOff, dRp, nRows, A->intBegin, A->intEnd, offs[0], offs[1], A->genIntBegin,
+                                                 A->genIntEnd, A->dGenRow, A->dGenLen);
+  const int64_t nSlices = A->nGen / 32;
+  MXG_LB_ALLOC(dSliceW, int32_t, nSlices);
+  MXG_LB_KEEP(A->dSlicePtr, int64_t, nSlices + 1);
+  if (nSlices > 0) k_lb_slice_width<<<lbGrid(nSlices), 256, 0, st>>>(A->dGenLen, nSlices, dSliceW);
+  int64_t totalW = 0;
+  MXG_CUDA(exclusiveScan(ctx, dSliceW, A->dSlicePtr, nSlices, &totalW));
+  k_lb_times32<<<lbGrid(nSlices + 1), 256, 0, st>>>(A->dSlicePtr, nSlices + 1);
+  A->ellEntries = totalW * 32;
+  MXG_LB_KEEP(A->dCol, int32_t, A->ellEntries);
+  T* dEllVal = nullptr;
+  MXG_LB_KEEP(dEllVal, T, A->ellEntries);
+  A->dVal = dEllVal;
+  if (nSlices > 0) k_lb_fill_ell<T><<<lbGrid(nSlices * 32), 256, 0, st>>>(A->dGenRow, A->dGenLen, A->dSlicePtr, dRp, dExt, dValG, base, nSlices, A->dCol, dEllVal);
+  ctx->launches += 5;
+
+  // ---- inverse diagonal for the smoothers (square operators on a single map only)
+  if (nRows == nLoc && A->rowMap->gids == A->domMap->gids) {
+    T* dInv = nullptr;
+    void* q = nullptr;
+    MXG_CUDA(cudaMalloc(&q, size_t(std::max<int64_t>(nRows, 1)) * sizeof(T)));
+    dInv = static_cast<T*>(q);
+    A->dInvDiag = dInv;
+    if (nRows > 0) k_lb_inv_diag<T><<<lbGrid(nRows), 256, 0, st>>>(dRp, dExt, dValG, base, nRows, dInv);
+    ctx->launches++;
+  }
+  MXG_CUDA(cudaGetLastError());
+  MXG_CUDA(cudaStreamSynchronize(st));
+  return MXG_OK;
+}
+
 }  // namespace
+
+namespace mxg {
+
+// rows [r0, r0 + rowMap->nLocal) of a device CRS (dRowptr points at row r0 and holds offsets into dCol / dVal; columns are
+// positions in the column field's map, of which domMap owns [colBegin, colBegin + nLocal)) -> device operator
+int crsCreateFromDevice(mxg_map* rowMap, mxg_map* domMap, const int64_t* dRowptr, const int32_t* dCol, const void* dVal, int64_t colBegin,
+                        int64_t colFieldSize, const int64_t* colFieldGids, int isComplex, int layout, mxg_crs** out) {
+  MXG_REQUIRE(rowMap && domMap && dRowptr && out, "mxg_crs_create_from_dcsr: NULL argument");
+  MXG_REQUIRE(rowMap->ctx == domMap->ctx, "mxg_crs_create_from_dcsr: maps live on different contexts");
+  MXG_REQUIRE(layout >= 0 && layout <= 1, "mxg_crs_create_from_dcsr: unknown layout %d", layout);
+  MXG_REQUIRE(rowMap->perm.empty() && domMap->perm.empty(), "mxg_crs_create_from_dcsr: ordered maps are not supported by the device layout builder");
+  mxg_ctx* ctx = rowMap->ctx;
+  MXG_CUDA(cudaSetDevice(ctx->device));
+  mxg_crs* A = new mxg_crs;
+  A->ctx = ctx;
+  A->rowMap = rowMap;
+  A->domMap = domMap;
+  rowMap->refs++;
+  domMap->refs++;
+  A->isComplex = isComplex != 0;
+  A->nRows = rowMap->nLocal;
+  A->nLoc = domMap->nLocal;
+  const int rc = A->isComplex ? buildFromDeviceImpl<zd>(A, dRowptr, dCol, dVal, colBegin, colFieldSize, colFieldGids, layout)
+                              : buildFromDeviceImpl<double>(A, dRowptr, dCol, dVal, colBegin, colFieldSize, colFieldGids, layout);
+  if (rc) {
+    mxg_crs_destroy(A);
+    return rc;
+  }
+  *out = A;
+  return MXG_OK;
+}
+
+}  // namespace mxg
 
 extern "C" {
 

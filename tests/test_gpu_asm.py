@@ -124,7 +124,7 @@ def test_errors_are_reported_not_swallowed(asm, ctx):
         p.map("bfield")                      # before setup
     p.setup()
     with pytest.raises(asm.AssemblyError):
-        p.op("curlE") @ p.op("curlE")
+        p.op("divB") @ p.op("divB")          # (psi x B) (psi x B): shapes do not chain
     with pytest.raises(asm.AssemblyError):
         api.sim(ctx.h, (0, 4, 4))
     with pytest.raises(asm.AssemblyError):
@@ -168,3 +168,67 @@ def test_eigensolve_on_a_problem_assembled_entirely_on_the_device(asm, mx, ctx, 
     np.testing.assert_allclose(ev, ref, rtol=1e-9)
     res, div = s.check(ep.divB, A=ep.curlCurl)
     assert np.all(res[:nev] < 1e-6) and np.all(div[:nev] < 1e-6)
+
+
+@pytest.mark.parametrize("case,name", [("pillbox", "curlCurl"), ("pillbox", "vecLapl"), ("pillbox", "divB"), ("crabcav", "curlCurl"),
+                                       ("bloch-pec", "vecLapl"), ("vacuum", "curlCurl")])
+def test_device_layout_builder_makes_the_layout_of_the_host_builder(asm, mx, ctx, orc, case, name, monkeypatch):
+    """mxg_crs_create_from_dcsr builds the operator layout with kernels (hash-table pattern dictionary, sliced ELL, inverse
+    diagonal). Same statistics as the host builder fed with the oracle's rows, same result as the host builder fed with the
+    device rows (MXG_LAYOUT_BUILD=host), bit-identical applies."""
+    from conftest import gpu_matrix
+    kw = dict(CASES[case])
+    if case == "pillbox":
+        kw["n"] = 20
+    o, p = gpu_pair(asm, ctx, orc, **kw)
+    H, op, rmap, cmap = gpu_matrix(mx, ctx, o, name)
+    rf, cf = {"curlCurl": ("bfield", "bfield"), "vecLapl": ("bfield", "bfield"), "divB": ("psifield", "bfield")}[name]
+    dr = asm.make_map(p, rf)
+    dc = dr if rf == cf else asm.make_map(p, cf)
+    d = p.op(name)
+    for layout in (0, 1):
+        Hl = mx.MxCrsMatrix.from_csr(rmap, cmap, *_global(op), layout=layout)
+        A = asm.to_crs(d, dr, dc, layout=layout)
+        monkeypatch.setenv("MXG_LAYOUT_BUILD", "host")
+        B = asm.to_crs(d, dr, dc, layout=layout)
+        monkeypatch.delenv("MXG_LAYOUT_BUILD")
+        assert A.stats() == Hl.stats() == B.stats(), (layout, A.stats(), Hl.stats(), B.stats())
+        x = mx.MxMultiVector(dc, 3, is_complex=op.is_complex)
+        x.random(31)
+        ys = []
+        for M in (A, B, Hl):
+            y = mx.MxMultiVector(dr, 3, is_complex=op.is_complex)
+            M.apply(x, y)
+            ys.append(y.to_host())
+        assert np.array_equal(ys[0], ys[1]) and np.array_equal(ys[0], ys[2]), layout
+    assert H.stats()["rows"] == d.nrows
+
+
+def _global(op):
+    rowptr, col, val = op.arrays()
+    _, cg = op.maps()
+    return rowptr, cg[col], val
+
+
+def test_smoothers_see_the_same_inverse_diagonal(asm, mx, ctx, orc):
+    """The V-cycle uses 1 / diag(A) kept with the operator: one multigrid application must give identical bits whether
+    the level operators were laid out by the host builder or on the device."""
+    sizes = [16, 8]
+    sims = [asm.example_sim(ctx, "pillbox", n) for n in sizes]
+    outs = []
+    for how in ("device", "host"):
+        if how == "host":
+            import os
+            os.environ["MXG_LAYOUT_BUILD"] = "host"
+        try:
+            ep = asm.EigenProblem(ctx, sims)
+        finally:
+            import os
+            os.environ.pop("MXG_LAYOUT_BUILD", None)
+        prec = mx.MxGeoMultigridPrec(ctx, ep.vops, ep.Rb, ep.Pb, smoother_sweeps=2)
+        b = mx.MxMultiVector(ep.bmaps[0], 2)
+        b.random(8)
+        x = b.Clone(2)
+        prec.ApplyInverse(b, x)
+        outs.append(x.to_host())
+    assert np.array_equal(outs[0], outs[1])
