@@ -15,9 +15,8 @@
  *   MxCrsMatrix::fillComplete on the result    -> mxg_crs_create_from_dcsr
  *
  * Results are bit-identical to the reference's host path as restated by the oracle: same entry order inside a row
- * (ascending local column), same order of the floating-point sums, no fused multiply-add. The dielectric
- * inverse-permittivity operator (MxYeeFitInvEps) stays host-generated; hand it in with mxg_dcsr_upload
- * and the chains around it run here.
+ * (ascending local column), same order of the floating-point sums, no fused multiply-add, complex quotients as
+ * libgcc's __divdc3 forms them. mxg_dcsr_upload brings a host-generated factor into the same algebra.
  *
  * Conventions as in mxgpu.h: plain C, opaque handles, int return codes (0 = ok), message via mxg_last_error(),
  * one host thread per context. Fields are named "bfield", "efield", "psifield". Boundary codes: 0 periodic, 1 zero,
@@ -69,8 +68,13 @@ int mxg_sim_create(mxg_ctx* ctx, const int n[3], const double origin[3], const d
 int mxg_sim_destroy(mxg_sim* sim);
 /* PEC region from a shape: edge / face / cell fractions of the three fields computed on the device (MxGridField.cpp:193-226) */
 int mxg_sim_set_pec_shape(mxg_sim* sim, const mxg_shape* shape);
-/* ... or handed in from a host MxGridField: (n0+3)(n1+3)(n2+3) cells of the guarded block x components, cell-major */
+/* ... or handed in from a host MxGridField: (n0+3)(n1+3)(n2+3) cells of the guarded block x components, cell-major
+ * (fields bfield, efield, psifield; dfield as well when dielectrics are present) */
 int mxg_sim_set_pec_fractions(mxg_sim* sim, const char* field, const double* fracs);
+/* MxEMSim::addDielectric (MxEMSim.cpp:134-148): a shape filled with the permittivity tensor eps (3x3 complex, row-major
+ * (re, im) pairs; up to 4 objects). Its edge / dual-face / cell fractions are computed on the device; the operators
+ * "invEps" (MxYeeFitInvEps.cpp:420-596) and "invEpsVolAve" (:650-725) become available and the chains use them. */
+int mxg_sim_add_dielectric(mxg_sim* sim, const mxg_shape* shape, const double eps[18]);
 int mxg_sim_setup(mxg_sim* sim); /* DOF maps of B, E and psi (MxGridField.cpp:256-297 with the Dey-Mittra overrides) */
 int mxg_sim_map_size(mxg_sim* sim, const char* field, int64_t* num_local, int64_t* num_global);
 int mxg_sim_map_copy(mxg_sim* sim, const char* field, int64_t* gids);
@@ -79,8 +83,9 @@ int mxg_sim_fractions(mxg_sim* sim, const char* field, double* out); /* guarded-
 int mxg_sim_make_map(mxg_sim* sim, const char* field, int64_t begin, int64_t end, mxg_map** out);
 
 /* ---- operators ---- */
-/* name: curlE curlB divB gradPsi dmA dmL dmVInv mRhs curlCurl gradDiv vecLapl scaLapl (MxEMOps.cpp:39-168,
- * MxMagWaveOp.cpp:137-245). inv_eps / inv_eps_vol_ave: optional dielectric factors (NULL without dielectrics). */
+/* name: curlE curlB divB gradPsi dmA dmL dmVInv mRhs invEps invEpsVolAve curlCurl gradDiv vecLapl scaLapl
+ * (MxEMOps.cpp:39-168, MxMagWaveOp.cpp:137-245). inv_eps / inv_eps_vol_ave: optional replacements for the dielectric
+ * factors of the chains (NULL: generated from the simulation's dielectric objects, identity without any). */
 int mxg_sim_op(mxg_sim* sim, const char* name, int is_complex, const mxg_dcsr* inv_eps, const mxg_dcsr* inv_eps_vol_ave,
                mxg_dcsr** out);
 int mxg_dcsr_upload(mxg_sim* sim, const char* row_field, const char* col_field, int64_t nrows, int64_t ncols,

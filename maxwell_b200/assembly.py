@@ -35,6 +35,7 @@ class AssemblyAPI:
             "sim_destroy": [vp],
             "sim_set_pec_fractions": [vp, C.c_char_p, vp],
             "sim_set_pec_shape": [vp, vp],
+            "sim_add_dielectric": [vp, vp, vp],
             "sim_setup": [vp],
             "sim_map_size": [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64)],
             "sim_map_copy": [vp, C.c_char_p, vp],
@@ -195,6 +196,18 @@ class Sim:
 
     def set_pec_shape(self, shape):
         self.api.call("sim_set_pec_shape", self.handle, shape.handle)
+        self._setup = False
+        return self
+
+    def add_dielectric(self, shape, eps):
+        """MxEMSim::addDielectric: a shape filled with the permittivity tensor eps (scalar, 3 diagonal values or 3x3, real or complex)."""
+        e = np.asarray(eps, dtype=np.complex128)
+        if e.ndim == 0:
+            e = np.eye(3) * e
+        elif e.ndim == 1:
+            e = np.diag(e)
+        e = np.ascontiguousarray(e.reshape(3, 3).astype(np.complex128))
+        self.api.call("sim_add_dielectric", self.handle, shape.handle, e.ctypes.data)
         self._setup = False
         return self
 
@@ -438,8 +451,13 @@ def crabcav_grid(cell_res=10, pad=2, num_cells=4, cell_len=2.0 * 0.0192, cav_rad
     return (nx, nx, nz), (-0.5 * lx, -0.5 * lx, -0.5 * lz), (lx, lx, lz)
 
 
-def example_sim(ctx, workload, n):
-    """The PEC-only workloads of bench.py as device simulations (set up, ready for op())."""
+# eps diag [10.225, 10.225, 9.95], off-diag [yz, xz, xy] = [0.6736.., -0.6736.., -0.825] (MxProblem.cpp:501-506)
+_S = 0.67360967926537398
+SAPPHIRE = np.array([[10.225, -0.825, -_S], [-0.825, 10.225, _S], [-_S, _S, 9.95]])
+
+
+def example_sim(ctx, workload, n, phase_shifts=None):
+    """The workloads of bench.py as device simulations (set up, ready for op())."""
     api = gpu_api()
     if workload == "pillbox":
         sim = gpu_sim(ctx, n, origin=(-0.5,) * 3, size=(1.0,) * 3)
@@ -450,9 +468,15 @@ def example_sim(ctx, workload, n):
         nn, origin, size = crabcav_grid(cell_res=max(2, (n - 4) // 4))
         sim = gpu_sim(ctx, nn, origin=origin, size=size)
         sim.set_pec_shape(crabcav_shape(api))
+    elif workload == "dsphmsph":      # example/dsphmsph.py: dielectric sphere (eps = 10) inside a PEC sphere
+        sim = gpu_sim(ctx, n, origin=(-0.5,) * 3, size=(1.0,) * 3)
+        sim.set_pec_shape(api.sphere(0.49, (0, 0, 0)))
+        sim.add_dielectric(api.sphere(0.37, (0, 0, 0)), 10.0)
+    elif workload == "phc":           # example/phc-sapph-r0.37.py: sapphire sphere in a periodic cell, Bloch phases
+        sim = gpu_sim(ctx, n, origin=(-0.5,) * 3, size=(1.0,) * 3, phase_shifts=phase_shifts or (0.0, 0.0, 0.0))
+        sim.add_dielectric(api.sphere(0.37, (0, 0, 0)), SAPPHIRE)
     else:
-        raise AssemblyError("workload %r has dielectrics: its inverse-permittivity operator is host-generated "
-                            "(upload it with Sim.upload and pass inv_eps= to op())" % workload)
+        raise AssemblyError("unknown workload %r" % workload)
     return sim.setup()
 
 

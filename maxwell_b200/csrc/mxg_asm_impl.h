@@ -15,6 +15,8 @@
 #include <vector>
 
 #include "mxg_yee.h"
+#include "mxg_shape.h"
+#include "mxg_eps.h"
 
 namespace mxa {
 
@@ -61,6 +63,13 @@ class Assembler {
       x_.free(const_cast<int32_t*>(h_.f[k].lidOf));
       x_.free(const_cast<int64_t*>(h_.f[k].gids));
     }
+    x_.free(const_cast<double*>(h_.f[mxy::FIELD_D].region));      // D borrows E's map
+    for (int d = 0; d < h_.numDiel; ++d) {
+      x_.free(const_cast<double*>(h_.diel[d].fracE));
+      x_.free(const_cast<double*>(h_.diel[d].fracD));
+      x_.free(const_cast<double*>(h_.diel[d].fracPsi));
+      x_.free(const_cast<void*>(h_.diel[d].shape));
+    }
     x_.free(h_.err);
     x_.free(dSim_);
   }
@@ -86,12 +95,12 @@ class Assembler {
     std::complex<double> phase[3];
     for (int i = 0; i < 3; ++i) phase[i] = std::exp(std::complex<double>(0.0, 1.0) * phaseShifts[i]);   // MxGridField.cpp:34-38
     complex_ = phaseShifts[0] != 0 || phaseShifts[1] != 0 || phaseShifts[2] != 0;
-    for (int k = 0; k < mxy::NUM_FIELDS; ++k) {
+    for (int k = 0; k < mxy::NUM_ALL_FIELDS; ++k) {
       mxy::Field& f = h_.f[k];
       f.kind = k;
       f.ncomp = k == mxy::FIELD_PSI ? 1 : 3;
       for (auto& r : f.xi) for (double& v : r) v = 0.0;
-      if (k == mxy::FIELD_E) {                       // MxYeeElecFieldBase.cpp:64-82
+      if (k == mxy::FIELD_E || k == mxy::FIELD_D) {  // MxYeeElecFieldBase.cpp:64-82 (D: same positions, MxYeeFitDField)
         f.xi[0][0] = 0.5 * dx; f.xi[1][1] = 0.5 * dy; f.xi[2][2] = 0.5 * dz;
       } else if (k == mxy::FIELD_B) {                // MxYeeMagFieldBase.cpp:85-116
         f.xi[0][1] = 0.5 * dy; f.xi[0][2] = 0.5 * dz;
@@ -149,11 +158,66 @@ class Assembler {
   }
   void regionChanged() { pushSim(); }
 
+  // PEC region from a shape: edge / face / cell fractions of B, E and psi computed on the executor
+  // (MxEMSim.cpp:122-129 -> MxGridField::addShapeRep, MxGridField.cpp:193-226)
+  void setPecShape(const Shape& shape) {
+    checkShape(shape);
+    ShapeNode* nodes = uploadShape(shape);
+    for (int k = 0; k < mxy::NUM_FIELDS; ++k) {
+      double* out = regionBuffer(k);
+      pushSim();
+      x_.forEach(mxy::numFullCells(h_.g), FractionCells{dSim_, nodes, k, out});
+    }
+    x_.sync();
+    x_.free(nodes);
+    pec_ = shape;
+    // fractions of the dual faces are only needed next to dielectrics; drop stale ones
+    x_.free(const_cast<double*>(h_.f[mxy::FIELD_D].region));
+    h_.f[mxy::FIELD_D].region = nullptr;
+    pushSim();
+  }
+
+  // MxEMSim::addDielectric + MxEMSim.cpp:134-148: fractions of the dielectric's shape on E, D and psi; eps = 3x3 complex
+  // tensor, row-major (re, im) pairs
+  void addDielectric(const Shape& shape, const double eps[18]) {
+    checkShape(shape);
+    if (h_.numDiel >= mxy::kMaxDielectrics) throw std::runtime_error("at most 4 dielectric objects");
+    mxy::DielectricRep& D = h_.diel[h_.numDiel];
+    ShapeNode* nodes = uploadShape(shape);
+    const int64_t cells = mxy::numFullCells(h_.g);
+    double* fe = x_.template alloc<double>(cells * 3);
+    double* fd = x_.template alloc<double>(cells * 3);
+    double* fp = x_.template alloc<double>(cells);
+    x_.forEach(cells, FractionCells{dSim_, nodes, mxy::FIELD_E, fe});
+    x_.forEach(cells, FractionCells{dSim_, nodes, mxy::FIELD_D, fd});
+    x_.forEach(cells, FractionCells{dSim_, nodes, mxy::FIELD_PSI, fp});
+    x_.sync();
+    D.fracE = fe; D.fracD = fd; D.fracPsi = fp;
+    D.shape = nodes;
+    bool offDiag = false;
+    for (int i = 0; i < 9; ++i) { D.epsRe[i] = eps[2 * i]; D.epsIm[i] = eps[2 * i + 1]; }
+    for (int i : {1, 2, 5}) offDiag = offDiag || D.epsRe[i] != 0.0 || D.epsIm[i] != 0.0;    // MxDielectric.cpp:27-36
+    D.isDiag = offDiag ? 0 : 1;
+    h_.numDiel++;
+    pushSim();
+  }
+  int numDielectrics() const { return h_.numDiel; }
+
   // MxGridField.cpp:256-297 for B, E and psi (B first: the others consult its rules)
   void setup() {
     if (hasPEC_)
       for (int k = 0; k < mxy::NUM_FIELDS; ++k)
         if (!h_.f[k].region) throw std::runtime_error("a PEC region needs fractions for the B, E and psi fields");
+    if (hasPEC_ && h_.numDiel > 0 && !h_.f[mxy::FIELD_D].region) {     // MxEMSim.cpp:122-129: the D field joins with dielectrics
+      if (pec_.nodes.empty()) throw std::runtime_error("dielectrics next to host-supplied PEC fractions need those of the D field too (dfield)");
+      ShapeNode* nodes = uploadShape(pec_);
+      double* out = x_.template alloc<double>(mxy::numFullCells(h_.g) * 3);
+      x_.forEach(mxy::numFullCells(h_.g), FractionCells{dSim_, nodes, mxy::FIELD_D, out});
+      x_.sync();
+      x_.free(nodes);
+      h_.f[mxy::FIELD_D].region = out;
+    }
+    h_.f[mxy::FIELD_D].regionSet = hasPEC_ ? 1 : 0;
     for (int k = 0; k < mxy::NUM_FIELDS; ++k) {
       mxy::Field& f = h_.f[k];
       x_.free(const_cast<int32_t*>(f.lidOf));
@@ -174,6 +238,10 @@ class Assembler {
       f.nLoc = total;
       pushSim();
     }
+    h_.f[mxy::FIELD_D].lidOf = h_.f[mxy::FIELD_E].lidOf;      // MxEMSim.cpp:186-190: D shares E's map
+    h_.f[mxy::FIELD_D].gids = h_.f[mxy::FIELD_E].gids;
+    h_.f[mxy::FIELD_D].nLoc = h_.f[mxy::FIELD_E].nLoc;
+    pushSim();
     checkErr("map set-up");
     setUp_ = true;
   }
@@ -348,6 +416,28 @@ class Assembler {
     if (name == "dmL") return generate<S>(GEN_FRACS, FIELD_E, false, 0.e-6);      // MxEMOps.cpp:61-63
     if (name == "dmVInv") return generate<S>(GEN_FRACS, FIELD_PSI, true, 0.e-6);  // MxEMOps.cpp:125-127
     if (name == "mRhs") return generate<S>(GEN_FRACS, FIELD_B, false, 0.e-12);    // MxMagWaveOp.cpp:227-241
+    if (name == "invEps" || name == "invEpsVolAve") {                              // MxEMOps.cpp:72-81
+      requireSetUp();
+      if (h_.numDiel == 0) throw std::runtime_error("the simulation has no dielectric objects");
+      Csr<S> m;
+      if (name == "invEps") {
+        m = buildRows<S>(h_.f[FIELD_E].nLoc, h_.f[FIELD_E].nLoc, InvEpsRow<S>{dSim_, hasPEC_ ? 1 : 0});
+        m.rowField = m.colField = FIELD_E;
+      } else {
+        m = buildRows<S>(h_.f[FIELD_PSI].nLoc, h_.f[FIELD_PSI].nLoc, InvEpsVolAveRow<S>{dSim_});
+        m.rowField = m.colField = FIELD_PSI;
+      }
+      checkErr("inverse permittivity");
+      return m;
+    }
+    // dielectric objects of the simulation supply the factors the caller did not hand in
+    Csr<S> ownEps, ownVol;
+    struct Owned {
+      Assembler* a; Csr<S>*x, *y;
+      ~Owned() { a->destroy(*x); a->destroy(*y); }
+    } owned{this, &ownEps, &ownVol};
+    if (h_.numDiel > 0 && (name == "curlCurl" || name == "vecLapl") && !invEps) { ownEps = buildOp<S>("invEps"); invEps = &ownEps; }
+    if (h_.numDiel > 0 && (name == "gradDiv" || name == "vecLapl") && !invEpsVolAve) { ownVol = buildOp<S>("invEpsVolAve"); invEpsVolAve = &ownVol; }
     if (name == "curlCurl") {                                                      // MxMagWaveOp.cpp:144-153
       Csr<S> m = generate<S>(GEN_CURL_B);
       if (invEps) replaceWith(m, multiply(*invEps, m));
@@ -428,6 +518,15 @@ class Assembler {
     return bc == PEC ? (normal ? CONSTANT : ZERO) : (normal ? ZERO : CONSTANT);                   // MxYeeElecFieldBase.cpp:104-133
   }
   void pushSim() { x_.toExec(dSim_, &h_, sizeof(mxy::Sim)); }
+  static void checkShape(const Shape& shape) {
+    if (shape.nodes.empty()) throw std::runtime_error("empty shape");
+    if (shape.depth() > kShapeMaxDepth) throw std::runtime_error("shape tree deeper than 8 levels");
+  }
+  ShapeNode* uploadShape(const Shape& shape) {
+    ShapeNode* d = x_.template alloc<ShapeNode>(int64_t(shape.nodes.size()));
+    x_.toExec(d, shape.nodes.data(), shape.nodes.size() * sizeof(ShapeNode));
+    return d;
+  }
   void requireSetUp() const {
     if (!setUp_) throw std::runtime_error("the simulation has not been set up (mxg_sim_setup)");
   }
@@ -440,6 +539,7 @@ class Assembler {
   X& x_;
   mxy::Sim h_;            // host copy; its pointers are executor pointers
   mxy::Sim* dSim_ = nullptr;
+  Shape pec_;             // kept for the D-field fractions a later dielectric needs
   bool hasPEC_ = false, setUp_ = false, complex_ = false;
 };
 

@@ -426,8 +426,8 @@ MXS_HD inline double boxFraction(const ShapeNode* sh, double lx, double ly, doub
 }
 
 // MxGridField.cpp:193-226 with calcCompFrac (MxGridField.hpp:186-191): fractions of every component of one cell of the
-// guarded block. E: edges (MxYeeFitEField.cpp:40-48), B: faces (MxYeeFitBField.cpp:52-58), psi: the cell box
-// (MxYeePsiField.cpp:64).
+// guarded block. E: edges (MxYeeFitEField.cpp:40-48), B: faces (MxYeeFitBField.cpp:52-58), D: the dual faces at the E
+// positions (MxYeeFitDField.cpp:53-58), psi: the cell box (MxYeePsiField.cpp:64).
 struct FractionCells {
   const mxy::Sim* sim;
   const ShapeNode* shape;
@@ -446,7 +446,7 @@ struct FractionCells {
       for (int k = 0; k < 3; ++k) p.v[k] = (g.origin[k] + double(nc[k]) * g.d[k]) + f.xi[comp][k];
       double fr;
       if (kind == mxy::FIELD_E) fr = segmentFraction(shape, comp, g.d[comp], p);
-      else if (kind == mxy::FIELD_B)
+      else if (kind == mxy::FIELD_B || kind == mxy::FIELD_D)
         fr = comp == 0 ? rectFraction(shape, 0, g.d[1], g.d[2], p)
            : comp == 1 ? rectFraction(shape, 1, g.d[2], g.d[0], p)
                        : rectFraction(shape, 2, g.d[0], g.d[1], p);
@@ -652,24 +652,6 @@ inline Shape makeRepeat(const Shape& shape, const double origin[3], const double
   s.root().par[7] = double(numPos);
   s.root().par[8] = double(-numNeg);
   return s;
-}
-
-// fractions of the three Yee fields for one PEC shape, on the executor (MxEMSim.cpp:122-129: B, E, psi)
-template <class AssemblerT>
-void computeFractions(AssemblerT& as, const Shape& shape) {
-  if (shape.nodes.empty()) throw std::runtime_error("empty shape");
-  if (shape.depth() > kShapeMaxDepth) throw std::runtime_error("shape tree deeper than 8 levels");
-  auto& x = as.exec();
-  ShapeNode* dNodes = x.template alloc<ShapeNode>(int64_t(shape.nodes.size()));
-  x.toExec(dNodes, shape.nodes.data(), shape.nodes.size() * sizeof(ShapeNode));
-  for (int k = 0; k < mxy::NUM_FIELDS; ++k) {
-    double* out = as.regionBuffer(k);
-    as.regionChanged();
-    x.forEach(mxy::numFullCells(as.sim().g), FractionCells{as.simOnExec(), dNodes, k, out});
-  }
-  x.sync();
-  x.free(dNodes);
-  as.regionChanged();
 }
 
 }  // namespace mxa

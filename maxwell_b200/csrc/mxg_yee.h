@@ -21,7 +21,10 @@
 namespace mxy {
 
 enum BCType { PERIODIC = 0, ZERO = 1, CONSTANT = 2, PEC = 3, PMC = 4 };
-enum FieldKind { FIELD_B = 0, FIELD_E = 1, FIELD_PSI = 2, NUM_FIELDS = 3 };
+// B, E and psi carry DOF maps; D (the dual-face field of the dielectric update, MxYeeFitDField) shares E's map and exists
+// only to hold face fractions and boundary factors at the E positions
+enum FieldKind { FIELD_B = 0, FIELD_E = 1, FIELD_PSI = 2, NUM_FIELDS = 3, FIELD_D = 3, NUM_ALL_FIELDS = 4 };
+constexpr int kMaxDielectrics = 4;
 enum FactorAction { ACT_NONE = 0, ACT_DIV = 1, ACT_MUL = 2, ACT_NEG = 3, ACT_ZERO = 4 };
 
 // complex scalar: (re, im), bit-compatible with std::complex<double>
@@ -60,10 +63,23 @@ struct Field {
   double facRe[125], facIm[125];
 };
 
+// MxDielectric: a shape with a (possibly anisotropic, possibly complex) permittivity tensor; fractions of the shape on the
+// E edges, the dual D faces and the psi cells of the guarded block (MxEMSim.cpp:134-148)
+struct DielectricRep {
+  const double* fracE;
+  const double* fracD;
+  const double* fracPsi;
+  const void* shape;        // flattened shape nodes on the executor (mxg_shape.h), for the interface normal
+  double epsRe[9], epsIm[9];
+  int isDiag;
+};
+
 struct Sim {
   Grid g;
-  Field f[NUM_FIELDS];
+  Field f[NUM_ALL_FIELDS];
   int* err;                 // set to non-zero by row functions that meet an impossible index
+  int numDiel;
+  DielectricRep diel[kMaxDielectrics];
 };
 
 // ---- indexing -------------------------------------------------------------------------------------------------
@@ -215,7 +231,7 @@ MXY_HD bool factorOf(const Sim& s, int kind, int comp, const int cell[3], double
   if (kind == FIELD_B && f.regionSet && regionFrac(s, f, comp, cell) < f.dmFrac) return false;
   if (f.regionSet && regionFrac(s, f, comp, cell) == 0.0) return false;
   const int code = factorCode(s.g, f, comp, cell);
-  if (kind != FIELD_B) {
+  if (kind == FIELD_E || kind == FIELD_PSI) {
     // The reference tests useCompInMap on the un-wrapped cell; by default the wrapped one is tested so the
     // wrap-around entry of a PERIODIC upper boundary survives.
     int c[3] = {cell[0], cell[1], cell[2]};

@@ -209,3 +209,51 @@ def test_grid_transfers_match_the_oracle(api, case):
         assert (rt.nrows, rt.ncols, rt.nnz) == (gt.nrows, gt.ncols, gt.nnz)
         for x, y in zip(rt.arrays(), gt.arrays()):
             assert np.array_equal(x, y), field
+
+
+DIELECTRIC_CASES = {
+    # example/dsphmsph.py: dielectric sphere eps = 10 inside a PEC sphere
+    "dsphmsph": dict(n=8, origin=(-0.5,) * 3, size=(1.0,) * 3, pec=lambda S: S.sphere(0.49, (0, 0, 0)),
+                     diels=[(lambda S: S.sphere(0.37, (0, 0, 0)), np.eye(3) * 10.0)]),
+    # example/run.py:15-28: the octant with PEC / PMC symmetry planes
+    "dsphmsph-octant": dict(n=7, origin=(0.0,) * 3, size=(0.5,) * 3, lower=(orc.PEC, orc.PMC, orc.PMC), upper=(orc.PEC,) * 3,
+                            pec=lambda S: S.sphere(0.49, (0, 0, 0)), diels=[(lambda S: S.sphere(0.37, (0, 0, 0)), np.eye(3) * 10.0)]),
+    # example/phc-sapph-r0.37.py: anisotropic sapphire sphere, periodic with Bloch phases (complex)
+    "phc-sapphire": dict(n=7, origin=(-0.5,) * 3, size=(1.0,) * 3, phase_shifts=(0.9, -0.4, 1.7),
+                         diels=[(lambda S: S.sphere(0.37, (0, 0, 0)), orc.SAPPHIRE)]),
+    # two objects, one with a complex (lossy) tensor, next to a PEC pillbox
+    "two-objects": dict(n=8, origin=(-0.5,) * 3, size=(1.0,) * 3, pec=pillbox_shape,
+                        diels=[(lambda S: S.sphere(0.2, (0.05, 0.0, -0.1)), orc.SAPPHIRE * (1.0 + 0.02j)),
+                               (lambda S: S.ellipsoid((-0.1, 0.1, 0.15), (0.12, 0.2, 0.1)), np.diag([2.0, 3.0, 4.5]))]),
+}
+
+
+def dielectric_pair(new_sim, api, n, origin, size, diels, pec=None, lower=None, upper=None, phase_shifts=None):
+    o = orc.Sim(n, origin=origin, size=size, lower=lower, upper=upper, phase_shifts=phase_shifts,
+                pec=pec(orc.Shape) if pec else None, dielectrics=[(shape(orc.Shape), eps) for shape, eps in diels])
+    p = new_sim(n, origin=origin, size=size, lower=lower, upper=upper, phase_shifts=phase_shifts)
+    if pec:
+        p.set_pec_shape(pec(api))
+    for shape, eps in diels:
+        p.add_dielectric(shape(api), eps)
+    p.setup()
+    return o, p
+
+
+@pytest.mark.parametrize("case", sorted(DIELECTRIC_CASES))
+def test_inverse_permittivity_and_dielectric_chains_match_the_oracle(api, case):
+    """MxYeeFitInvEps: 9-point anisotropic rows from the edge / dual-face fractions and the interface normal, the
+    cell-averaged scalar 1 / eps, and the chains that contain them."""
+    kw = DIELECTRIC_CASES[case]
+    o, p = dielectric_pair(lambda n, **k: api.sim(None, n, **k), api, **kw)
+    cx = bool(kw.get("phase_shifts")) or any(np.iscomplexobj(e) for _, e in kw["diels"])
+    for f in asm.FIELDS:
+        assert np.array_equal(o.map(f), p.map(f)), f
+    for name in ("invEps", "invEpsVolAve", "curlCurl", "gradDiv", "vecLapl"):
+        a, b = o.op(name, is_complex=cx), p.op(name, is_complex=cx)
+        assert (a.nrows, a.ncols, a.nnz) == (b.nrows, b.ncols, b.nnz), name
+        for x, y in zip(a.arrays(), b.arrays()):
+            assert np.array_equal(x, y), name
+    if cx and not any(np.iscomplexobj(e) for _, e in kw["diels"]):
+        for x, y in zip(o.op("invEps", is_complex=False).arrays(), p.op("invEps", is_complex=False).arrays()):
+            assert np.array_equal(x, y)

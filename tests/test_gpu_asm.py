@@ -6,7 +6,7 @@ sources without a GPU; here the CUDA kernels run.
 import numpy as np
 import pytest
 
-from test_asm_replay import CASES, OPS, both, pillbox_shape, crabcav_shape, crab_grid  # noqa: F401
+from test_asm_replay import CASES, DIELECTRIC_CASES, OPS, both, dielectric_pair, pillbox_shape, crabcav_shape, crab_grid  # noqa: F401
 
 pytestmark = pytest.mark.gpu
 
@@ -232,3 +232,33 @@ def test_smoothers_see_the_same_inverse_diagonal(asm, mx, ctx, orc):
         prec.ApplyInverse(b, x)
         outs.append(x.to_host())
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("case", sorted(DIELECTRIC_CASES))
+def test_inverse_permittivity_assembled_on_the_device(asm, mx, ctx, orc, case):
+    """MxYeeFitInvEps on the device: anisotropic 9-point rows (3x3 complex inversions with libgcc's division order,
+    interface normals from the shape gradient), the scalar cell average, and the chains through them -- bit for bit."""
+    kw = DIELECTRIC_CASES[case]
+    o, p = dielectric_pair(lambda n, **k: asm.gpu_sim(ctx, n, **k), asm.gpu_api(), **kw)
+    cx = bool(kw.get("phase_shifts")) or any(np.iscomplexobj(e) for _, e in kw["diels"])
+    for name in ("invEps", "invEpsVolAve", "curlCurl", "gradDiv", "vecLapl"):
+        a, b = o.op(name, is_complex=cx), p.op(name, is_complex=cx)
+        assert (a.nrows, a.ncols, a.nnz) == (b.nrows, b.ncols, b.nnz), name
+        for x, y in zip(a.arrays(), b.arrays()):
+            bad = np.flatnonzero(x != y)
+            assert bad.size == 0, "%s: %d of %d entries differ, first %r vs %r" % (name, bad.size, x.size, x[bad[:1]], y[bad[:1]])
+    # and the assembled operator applies like the oracle's (K-form order when complex)
+    bmap = asm.make_map(p, "bfield")
+    A = asm.to_crs(p.op("vecLapl", is_complex=cx), bmap, bmap)
+    x = mx.MxMultiVector(bmap, 2, is_complex=cx)
+    x.random(5)
+    y = mx.MxMultiVector(bmap, 2, is_complex=cx)
+    A.apply(x, y)
+    ref = o.op("vecLapl", is_complex=cx)
+    xh, got = x.to_host(), y.to_host()
+    if cx:
+        K = ref.kform()
+        for j in range(2):
+            assert np.array_equal(K.apply(np.ascontiguousarray(xh[:, j]).view(np.float64)).view(np.complex128), got[:, j])
+    else:
+        assert np.array_equal(ref.apply(xh), got)
