@@ -30,13 +30,15 @@ def main():
     timed("dielectric_fractions_s", lambda: sim.add_dielectric(api.sphere(0.37, (0, 0, 0)), asm.SAPPHIRE))
     timed("maps_s", lambda: sim.setup())
     out["dofs"] = {f: sim.map_size(f)[0] for f in asm.FIELDS}
+    cc = None
     for name in ("invEps", "curlCurl", "vecLapl"):
         m = timed("op_%s_s" % name, lambda name=name: sim.op(name))
         out["nnz_" + name] = m.nnz
-        if name != "curlCurl":
-            del m
+        if name == "curlCurl":
+            cc = m
+    del m
     bmap = asm.make_map(sim, "bfield")
-    A = timed("layout_s", lambda: asm.to_crs(m, bmap, bmap))
+    A = timed("layout_s", lambda: asm.to_crs(cc, bmap, bmap))
     out["layout"] = A.stats()
     print(json.dumps(out))
 
