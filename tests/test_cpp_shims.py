@@ -69,3 +69,17 @@ def test_solver_driver_on_host_multivector(tmp_path, mx):
                            "-Wl,-rpath," + libdir])
     res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "PASSED" in res.stdout, res.stdout + res.stderr
+
+
+def test_assembly_shims(tmp_path, mx):
+    """include/mx/MxAssembly.hpp (MxShape / MxEMSim / MxDeviceCrs over include/mxasm.h): shapes are host objects and are
+    checked everywhere; without a device the simulation must fail loudly, with one the program assembles and applies a
+    small curl-curl operator two ways."""
+    exe = str(tmp_path / "asm_shim_check")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    libdir = os.path.dirname(mx.library_path())
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "asm_shim_check.cpp"), "-o", exe, "-L", libdir, "-lmxgpu",
+                           "-Wl,-rpath," + libdir])
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and "PASSED" in res.stdout, res.stdout + res.stderr
