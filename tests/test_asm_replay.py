@@ -257,3 +257,95 @@ def test_inverse_permittivity_and_dielectric_chains_match_the_oracle(api, case):
     if cx and not any(np.iscomplexobj(e) for _, e in kw["diels"]):
         for x, y in zip(o.op("invEps", is_complex=False).arrays(), p.op("invEps", is_complex=False).arrays()):
             assert np.array_equal(x, y)
+
+
+def random_shape_builder(seed):
+    """A seeded random CSG tree (primitives, placements, composites up to depth 4) as a function of the shape factory, so the
+    oracle and the product build the very same solid."""
+    def build(S):
+        rng = np.random.default_rng(seed)
+
+        def vec(scale=1.0):
+            return tuple(float(v) for v in rng.uniform(-scale, scale, 3))
+
+        def axis():
+            v = rng.normal(size=3)
+            return tuple(float(x) for x in v / np.linalg.norm(v))
+
+        def primitive():
+            k = int(rng.integers(0, 7))
+            if k == 0:
+                return S.cylinder(float(rng.uniform(0.1, 0.3)), axis(), vec(0.2))
+            if k == 1:
+                return S.sphere(float(rng.uniform(0.15, 0.35)), vec(0.2))
+            if k == 2:
+                return S.halfspace(vec(0.1), axis())
+            if k == 3:
+                return S.slab(float(rng.uniform(0.2, 0.5)), axis(), vec(0.1))
+            if k == 4:
+                return S.ellipsoid(vec(0.15), tuple(float(v) for v in rng.uniform(0.1, 0.35, 3)))
+            if k == 5:
+                return S.torus(float(rng.uniform(0.2, 0.3)), float(rng.uniform(0.05, 0.1)), axis(), vec(0.1))
+            return S.cone(float(rng.uniform(0.3, 0.8)), axis(), vec(0.3))
+
+        def place(s):
+            k = int(rng.integers(0, 6))
+            if k == 0:
+                s.translate(vec(0.1))
+            elif k == 1:
+                s.rotate(axis(), float(rng.uniform(-1.5, 1.5)))
+            elif k == 2:
+                s.rotate(axis(), float(rng.uniform(-1.5, 1.5)), pivot=vec(0.2))
+            elif k == 3:
+                s.scale(tuple(float(v) for v in rng.uniform(0.7, 1.4, 3)), origin=vec(0.1))
+            elif k == 4:
+                s.reflect(axis(), vec(0.1))
+            return s
+
+        def tree(depth):
+            if depth == 0 or rng.uniform() < 0.25:
+                return place(primitive())
+            k = int(rng.integers(0, 5))
+            if k == 0:
+                return place(S.intersection([tree(depth - 1), tree(depth - 1)]))
+            if k == 1:
+                return place(S.union([tree(depth - 1), tree(depth - 1), tree(depth - 1)]))
+            if k == 2:
+                return place(S.subtract(tree(depth - 1), [tree(depth - 1)]))
+            if k == 3:
+                return S.mirror(tree(depth - 1), axis(), vec(0.05))
+            return S.repeat(tree(depth - 1), vec(0.05), axis(), float(rng.uniform(0.3, 0.6)), 1, 1)
+
+        return tree(3)
+    return build
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_csg_trees_fractions_and_operators(api, seed):
+    """Eight random CSG solids: implicit function, gradient, edge / face / cell fractions, maps and the curl-curl chain agree
+    with the oracle to the last bit."""
+    build = random_shape_builder(1000 + seed)
+    so, sp = both(api, build)
+    rng = np.random.default_rng(seed)
+    for p in rng.uniform(-0.5, 0.5, size=(200, 3)):
+        assert so.func(p) == sp.func(p)
+        assert np.array_equal(np.asarray(so.grad(p)), sp.grad(p))
+    o, p = make_pair(api, n=(7, 6, 8), origin=(-0.5,) * 3, size=(1.0,) * 3, shape=build)
+    for f in asm.FIELDS:
+        assert np.array_equal(o.full_fracs(f), p.fracs(f)), f
+        assert np.array_equal(o.map(f), p.map(f)), f
+    if len(o.map("bfield")) > 0:
+        for name in ("curlCurl", "vecLapl", "scaLapl"):
+            for x, y in zip(o.op(name).arrays(), p.op(name).arrays()):
+                assert np.array_equal(x, y), name
+
+
+def test_too_deep_shapes_are_rejected(api):
+    s = api.sphere(0.3, (0, 0, 0))
+    for _ in range(8):
+        s = api.intersection([s, api.halfspace((0, 0, 0.2), (0, 0, -1))])
+    p = api.sim(None, 4, origin=(-0.5,) * 3, size=(1.0,) * 3)
+    with pytest.raises(asm.AssemblyError):
+        p.set_pec_shape(s)
+    with pytest.raises(asm.AssemblyError):
+        s.func((0, 0, 0))

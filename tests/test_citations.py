@@ -14,6 +14,9 @@ CITE = re.compile(r"\b((?:src/|example/|test/)?Mx[A-Za-z0-9_]+\.(?:cpp|hpp|h)|(?
 def _sources():
     out = []
     for rel in ("include/mxgpu.h", "include/mxsolver.h", "include/mx/MxTypes.hpp", "include/mx/MxLinAlg.hpp", "include/mx/MxSolver.hpp",
+                "include/mxasm.h", "include/mx/MxAssembly.hpp", "maxwell_b200/csrc/mxg_yee.h", "maxwell_b200/csrc/mxg_shape.h",
+                "maxwell_b200/csrc/mxg_eps.h", "maxwell_b200/csrc/mxg_asm_impl.h", "maxwell_b200/csrc/mxg_asm_api.inc",
+                "maxwell_b200/csrc/mxg_asm.cu", "maxwell_b200/assembly.py",
                 "oracle/mxo_geom.hpp", "oracle/mxo_sim.hpp", "oracle/mxo_ops.hpp", "oracle/oracle.py", "DESIGN.md", "INTEGRATION.md"):
         out.append(rel)
     return out
