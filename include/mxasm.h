@@ -65,7 +65,7 @@ int mxg_shape_destroy(mxg_shape* s);
  * (NULL = 0; non-zero shifts make operators complex by default), Dey-Mittra area-fraction cut-off (MxYeeFitBField). */
 int mxg_sim_create(mxg_ctx* ctx, const int n[3], const double origin[3], const double size[3], const int lower[3],
                    const int upper[3], const double phase_shifts[3], double dm_frac, int literal_upper_periodic_e, mxg_sim** out);
-int mxg_sim_destroy(mxg_sim* sim);
+int mxg_sim_destroy(mxg_sim* sim); /* destroy the mxg_dcsr matrices made from a simulation before the simulation itself */
 /* PEC region from a shape: edge / face / cell fractions of the three fields computed on the device (MxGridField.cpp:193-226) */
 int mxg_sim_set_pec_shape(mxg_sim* sim, const mxg_shape* shape);
 /* ... or handed in from a host MxGridField: (n0+3)(n1+3)(n2+3) cells of the guarded block x components, cell-major

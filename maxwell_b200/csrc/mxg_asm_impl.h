@@ -53,6 +53,18 @@ struct StoreInt {
   MXY_HD void operator()(int64_t i) const { out[i] = fn(i); }
 };
 
+// executor memory released at scope exit (temporaries of the passes below; an exception must not leak them)
+template <class X, class T>
+struct Scoped {
+  X& x;
+  T* p;
+  Scoped(X& exec, int64_t n) : x(exec), p(exec.template alloc<T>(n)) {}
+  ~Scoped() { x.free(p); }
+  Scoped(const Scoped&) = delete;
+  Scoped& operator=(const Scoped&) = delete;
+  T* release() { T* q = p; p = nullptr; return q; }
+};
+
 template <class X>
 class Assembler {
  public:
@@ -144,7 +156,6 @@ class Assembler {
     const int64_t n = mxy::numFullCells(h_.g) * f.ncomp;
     double* d = regionBuffer(kind);
     x_.toExec(d, fracs, size_t(n) * sizeof(double));
-    (void)f;
     pushSim();
   }
   // the executor-side fraction array of a field (filled by the fraction kernels)
@@ -224,17 +235,16 @@ class Assembler {
       x_.free(const_cast<int64_t*>(f.gids));
       f.lidOf = nullptr; f.gids = nullptr; f.nLoc = 0;
       const int64_t n = mxy::numNodes(h_.g) * f.ncomp;
-      int32_t* flag = x_.template alloc<int32_t>(n);
-      int64_t* off = x_.template alloc<int64_t>(n + 1);
-      x_.forEach(n, mxy::MapFlags{dSim_, k, flag});
-      const int64_t total = x_.scan(flag, off, n);
-      int32_t* lid = x_.template alloc<int32_t>(n);
-      int64_t* gids = x_.template alloc<int64_t>(total > 0 ? total : 1);
-      x_.forEach(n, mxy::MapFill{flag, off, lid, gids});
-      x_.free(flag);
-      x_.free(off);
-      f.lidOf = lid;
-      f.gids = gids;
+      Scoped<X, int32_t> flag(x_, n);
+      Scoped<X, int64_t> off(x_, n + 1);
+      x_.forEach(n, mxy::MapFlags{dSim_, k, flag.p});
+      const int64_t total = x_.scan(flag.p, off.p, n);
+      Scoped<X, int32_t> lid(x_, n);
+      Scoped<X, int64_t> gids(x_, total > 0 ? total : 1);
+      x_.forEach(n, mxy::MapFill{flag.p, off.p, lid.p, gids.p});
+      x_.sync();
+      f.lidOf = lid.release();
+      f.gids = gids.release();
       f.nLoc = total;
       pushSim();
     }
@@ -266,25 +276,27 @@ class Assembler {
   Csr<S> buildRows(int64_t nrows, int64_t ncols, const RowFn& fn) {
     Csr<S> m;
     m.nrows = nrows; m.ncols = ncols;
-    int32_t* cnt = x_.template alloc<int32_t>(nrows > 0 ? nrows : 1);
-    x_.forEach(nrows, mxy::CountRows<S, RowFn>{fn, cnt});
-    m.rowptr = x_.template alloc<int64_t>(nrows + 1);
-    m.nnz = x_.scan(cnt, m.rowptr, nrows);
-    x_.free(cnt);
-    m.col = x_.template alloc<int32_t>(m.nnz > 0 ? m.nnz : 1);
-    m.val = x_.template alloc<S>(m.nnz > 0 ? m.nnz : 1);
-    x_.forEach(nrows, mxy::FillRows<S, RowFn>{fn, m.rowptr, m.col, m.val});
+    Scoped<X, int64_t> rowptr(x_, nrows + 1);
+    {
+      Scoped<X, int32_t> cnt(x_, nrows > 0 ? nrows : 1);
+      x_.forEach(nrows, mxy::CountRows<S, RowFn>{fn, cnt.p});
+      m.nnz = x_.scan(cnt.p, rowptr.p, nrows);
+    }
+    Scoped<X, int32_t> col(x_, m.nnz > 0 ? m.nnz : 1);
+    Scoped<X, S> val(x_, m.nnz > 0 ? m.nnz : 1);
+    x_.forEach(nrows, mxy::FillRows<S, RowFn>{fn, rowptr.p, col.p, val.p});
+    m.rowptr = rowptr.release();
+    m.col = col.release();
+    m.val = val.release();
     return m;
   }
 
   template <class Fn>
   int maxOverRows(int64_t nrows, const Fn& fn) {
     if (nrows == 0) return 0;
-    int32_t* tmp = x_.template alloc<int32_t>(nrows);
-    x_.forEach(nrows, StoreInt<Fn>{fn, tmp});
-    const int m = x_.maxOf(tmp, nrows);
-    x_.free(tmp);
-    return m;
+    Scoped<X, int32_t> tmp(x_, nrows);
+    x_.forEach(nrows, StoreInt<Fn>{fn, tmp.p});
+    return x_.maxOf(tmp.p, nrows);
   }
 
   template <class S>
@@ -355,17 +367,20 @@ class Assembler {
     Csr<S> T;
     T.nrows = A.ncols; T.ncols = A.nrows; T.nnz = A.nnz;
     T.rowField = A.colField; T.colField = A.rowField;
-    int32_t* cnt = x_.template alloc<int32_t>(T.nrows > 0 ? T.nrows : 1);
-    x_.zero(cnt, size_t(T.nrows) * sizeof(int32_t));
-    x_.forEach(A.nnz, mxy::TransposeCount{A.col, cnt});
-    T.rowptr = x_.template alloc<int64_t>(T.nrows + 1);
-    x_.scan(cnt, T.rowptr, T.nrows);
-    x_.zero(cnt, size_t(T.nrows) * sizeof(int32_t));
-    T.col = x_.template alloc<int32_t>(T.nnz > 0 ? T.nnz : 1);
-    T.val = x_.template alloc<S>(T.nnz > 0 ? T.nnz : 1);
-    x_.forEach(A.nrows, mxy::TransposeFill<S>{A.view(), T.rowptr, cnt, T.col, T.val});
-    x_.forEach(T.nrows, mxy::SortRowInPlace<S>{T.rowptr, T.col, T.val});
-    x_.free(cnt);
+    Scoped<X, int32_t> cnt(x_, T.nrows > 0 ? T.nrows : 1);
+    Scoped<X, int64_t> rowptr(x_, T.nrows + 1);
+    Scoped<X, int32_t> col(x_, T.nnz > 0 ? T.nnz : 1);
+    Scoped<X, S> val(x_, T.nnz > 0 ? T.nnz : 1);
+    x_.zero(cnt.p, size_t(T.nrows) * sizeof(int32_t));
+    x_.forEach(A.nnz, mxy::TransposeCount{A.col, cnt.p});
+    x_.scan(cnt.p, rowptr.p, T.nrows);
+    x_.zero(cnt.p, size_t(T.nrows) * sizeof(int32_t));
+    x_.forEach(A.nrows, mxy::TransposeFill<S>{A.view(), rowptr.p, cnt.p, col.p, val.p});
+    x_.forEach(T.nrows, mxy::SortRowInPlace<S>{rowptr.p, col.p, val.p});
+    x_.sync();                       // cnt is released on return
+    T.rowptr = rowptr.release();
+    T.col = col.release();
+    T.val = val.release();
     return T;
   }
 
