@@ -349,3 +349,53 @@ def test_too_deep_shapes_are_rejected(api):
         p.set_pec_shape(s)
     with pytest.raises(asm.AssemblyError):
         s.func((0, 0, 0))
+
+
+def test_crs_algebra_on_general_matrices_against_scipy(api):
+    """multiply / add / transpose / purge on random sparse matrices that are no stencils (rows of 0 .. 40 entries, products
+    with up to a few hundred terms per row): pattern equal to scipy's, values to rounding."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(11)
+    sim = api.sim(None, 2)
+
+    def rand(m, n, density):
+        a = sp.random(m, n, density=density, random_state=rng, format="csr", dtype=np.float64)
+        a.sort_indices()
+        return a
+
+    def up(a):
+        return sim.upload(None, None, a.indptr.astype(np.int64), a.indices.astype(np.int32), a.data, ncols=a.shape[1])
+
+    def same(d, ref, exact_values=False):
+        ref = ref.tocsr()
+        ref.sort_indices()
+        rowptr, col, val = d.arrays()
+        assert np.array_equal(rowptr, ref.indptr) and np.array_equal(col, ref.indices)
+        if exact_values:
+            assert np.array_equal(val, ref.data)
+        else:
+            np.testing.assert_allclose(val, ref.data, rtol=1e-13, atol=1e-15)
+
+    A, B, C = rand(300, 200, 0.05), rand(200, 250, 0.08), rand(300, 200, 0.03)
+    dA, dB, dC = up(A), up(B), up(C)
+    same(dA @ dB, A @ B)
+    same(dA.add(2.0, dC, -0.5), 2.0 * A - 0.5 * C)
+    same(dA.transpose(), A.T, exact_values=True)
+    same((dA @ dB).transpose(scale=0.125), 0.125 * (A @ B).T)
+    small = A.copy()
+    small.data[::3] = 1e-13
+    kept = small.copy()
+    kept.data[np.abs(kept.data) <= 1e-12] = 0.0
+    kept.eliminate_zeros()
+    same(up(small).purge(), kept, exact_values=True)
+    wide_a, wide_b = rand(80, 60, 0.08), rand(60, 400, 0.04)      # ~10 x ~25 terms per row: beyond the 160-entry row table
+    same(up(wide_a) @ up(wide_b), wide_a @ wide_b)
+    with pytest.raises(asm.AssemblyError):                        # the stated limit: no product row beyond 400 terms
+        up(rand(50, 60, 0.6)) @ up(rand(60, 500, 0.5))
+    # complex
+    Z = rand(120, 90, 0.1).astype(np.complex128)
+    Z.data = Z.data + 1j * rng.uniform(-1, 1, Z.nnz)
+    Y = rand(90, 70, 0.1).astype(np.complex128)
+    Y.data = Y.data * (0.3 - 0.8j)
+    same(up(Z) @ up(Y), Z @ Y)
+    same(up(Z).transpose(), Z.conj().T, exact_values=True)
