@@ -6,7 +6,8 @@ sources without a GPU; here the CUDA kernels run.
 import numpy as np
 import pytest
 
-from test_asm_replay import CASES, DIELECTRIC_CASES, OPS, both, dielectric_pair, pillbox_shape, crabcav_shape, crab_grid  # noqa: F401
+from test_asm_replay import (CASES, DIELECTRIC_CASES, OPS, both, check_against_independent_fixtures, dielectric_pair,  # noqa: F401
+                             pillbox_shape, crabcav_shape, crab_grid)
 
 pytestmark = pytest.mark.gpu
 
@@ -262,3 +263,9 @@ def test_inverse_permittivity_assembled_on_the_device(asm, mx, ctx, orc, case):
             assert np.array_equal(K.apply(np.ascontiguousarray(xh[:, j]).view(np.float64)).view(np.complex128), got[:, j])
     else:
         assert np.array_equal(ref.apply(xh), got)
+
+
+def test_device_assembly_against_fixtures_independent_of_the_oracle(asm, ctx):
+    """The scipy Kronecker-product vacuum curl-curl and the analytic vacuum spectrum of tests/golden/ (no code shared with
+    the oracle), plus div curl = 0 and curlCurl grad = 0 on the cut-cell pillbox."""
+    check_against_independent_fixtures(lambda n, **k: asm.gpu_sim(ctx, n, **k))
